@@ -1,0 +1,236 @@
+/*
+ * scenes.cpp -- the reference's scene functions (raytracer/src/scene.rs) written against the
+ * C++ constructor mirror, plus the cameras of the BASELINE.json configs (main.rs:43-78 holds
+ * only the wwscene camera; the others are the RTIOW book cameras).
+ * Random draws follow the order of the reference's code; `rand::thread_rng()` is the scene
+ * stream of rt::Scene.
+ */
+#include "rt_host.h"
+
+#include <cmath>
+
+namespace rt {
+
+SceneLists random_scene(Scene &s) { // scene.rs:22-84
+    SceneLists out;
+    HittableList &world = out.world;
+
+    Tex checker = CheckerTexture::new_(s, Color::new_(0.2, 0.3, 0.1), Color::new_(0.9, 0.9, 0.9));
+    world.add(Sphere::new_(s, Point3::new_(0., -1000., 0.), 1000., Lambertian::new_arc(s, checker)));
+
+    for (int a = -11; a <= 11; ++a) {
+        for (int b = -11; b <= 11; ++b) {
+            double choose_mat = s.gen();
+            double cx = (double)a + 0.9 * s.gen();
+            double cz = (double)b + 0.9 * s.gen();
+            Point3 center = Point3::new_(cx, 0.2, cz);
+
+            if ((center - Point3::new_(4., 0.2, 0.)).length() > 0.9) {
+                if (choose_mat < 0.80) {
+                    Color albedo = s.random_vec(0., 1.);
+                    Point3 center2 = center + Vec3::new_(0., s.gen_range(0.0, 0.5), 0.);
+                    world.add(MovingSphere::new_(s, center, center2, 0.0, 1.0, 0.2, Lambertian::new_(s, albedo)));
+                } else if (choose_mat < 0.95) {
+                    Color albedo = s.random_vec(0.5, 1.);
+                    double fuzz = s.gen_range(0.0, 0.5);
+                    world.add(Sphere::new_(s, center, 0.2, Metal::new_(s, albedo, fuzz)));
+                } else {
+                    world.add(Sphere::new_(s, center, 0.2, Dielectric::new_(s, 1.5)));
+                }
+            }
+        }
+    }
+
+    world.add(Sphere::new_(s, Point3::new_(0., 1., 0.), 1., Dielectric::new_(s, 1.5)));
+    world.add(Sphere::new_(s, Point3::new_(-4., 1., 0.), 1., Lambertian::new_(s, Color::new_(0.4, 0.2, 0.1))));
+    world.add(Sphere::new_(s, Point3::new_(4., 1., 0.), 1., Metal::new_(s, Color::new_(0.7, 0.6, 0.5), 0.)));
+    return out; // no lights list upstream
+}
+
+SceneLists cornell_box(Scene &s) { // scene.rs:165-196
+    SceneLists out;
+    Mat light_strong = DiffuseLight::new_(s, Color::new_(60., 60., 60.));
+    Obj light_top = XZRect::new_(s, 213.0, 343.0, 127.0, 232.0, 554.0, light_strong);
+    out.world.add(FlipFace::new_(s, light_top));
+
+    Mat red = Lambertian::new_(s, Color::new_(0.65, 0.05, 0.05));
+    Mat white = Lambertian::new_(s, Color::new_(0.73, 0.73, 0.73));
+    Mat green = Lambertian::new_(s, Color::new_(0.12, 0.45, 0.15));
+
+    out.world.add(YZRect::new_(s, 0., 555., 0., 555., 555., red));
+    out.world.add(YZRect::new_(s, 0., 555., 0., 555., 0., green));
+    out.world.add(XZRect::new_(s, 0., 555., 0., 555., 0., white));
+    out.world.add(XZRect::new_(s, 0., 555., 0., 555., 555., white));
+    out.world.add(XYRect::new_(s, 0., 555., 0., 555., 555., white));
+
+    out.lights.add(light_top);
+    return out;
+}
+
+SceneLists cornell_smoke(Scene &s) { // scene.rs:199-257
+    SceneLists out;
+    HittableList &world = out.world;
+    Mat red = Lambertian::new_(s, Color::new_(0.65, 0.05, 0.05));
+    Mat white = Lambertian::new_(s, Color::new_(0.73, 0.73, 0.73));
+    Mat green = Lambertian::new_(s, Color::new_(0.12, 0.45, 0.15));
+    Mat light = DiffuseLight::new_(s, Color::new_(7., 7., 7.));
+
+    world.add(YZRect::new_(s, 0., 555., 0., 555., 555., green));
+    world.add(YZRect::new_(s, 0., 555., 0., 555., 0., red));
+    Obj light_rect = XZRect::new_(s, 113., 443., 127., 432., 554., light);
+    world.add(FlipFace::new_(s, light_rect));
+    world.add(XZRect::new_(s, 0., 555., 0., 555., 555., white));
+    world.add(XZRect::new_(s, 0., 555., 0., 555., 0., white));
+    world.add(XYRect::new_(s, 0., 555., 0., 555., 555., white));
+
+    Obj box1 = Boxes::new_(s, Point3::new_(0., 0., 0.), Point3::new_(165., 330., 165.), white);
+    box1 = RotateY::new_(s, box1, 15.);
+    box1 = Translate::new_(s, box1, Vec3::new_(265., 0., 295.));
+    world.add(ConstantMedium::new_(s, box1, 0.01, Color::new_(0., 0., 0.)));
+
+    Obj box2 = Boxes::new_(s, Point3::new_(0., 0., 0.), Point3::new_(165., 165., 165.), white);
+    box2 = RotateY::new_(s, box2, -18.);
+    box2 = Translate::new_(s, box2, Vec3::new_(130., 0., 65.));
+    world.add(ConstantMedium::new_(s, box2, 0.01, Color::new_(1., 1., 1.)));
+
+    out.lights.add(light_rect); // upstream returns no lights list; same rule as final_scene (Q12)
+    return out;
+}
+
+SceneLists final_scene(Scene &s, const SceneOptions &o) { // scene.rs:260-362
+    SceneLists out;
+    HittableList box1;
+    Mat ground = Lambertian::new_(s, Color::new_(0.48, 0.83, 0.53));
+
+    const int boxes_per_side = 20;
+    for (int i = 0; i < boxes_per_side; ++i) {
+        for (int j = 0; j < boxes_per_side; ++j) {
+            double w = 100.;
+            double x0 = -1000. + (double)i * w;
+            double z0 = -1000. + (double)j * w;
+            double y0 = 0.;
+            double x1 = x0 + w;
+            double y1 = s.gen_range(1.0, 101.0);
+            double z1 = z0 + w;
+            box1.add(Boxes::new_(s, Point3::new_(x0, y0, z0), Point3::new_(x1, y1, z1), ground));
+        }
+    }
+
+    HittableList &world = out.world;
+    world.add(BvhNode::new_list(s, box1, 0., 1.));
+
+    Mat light = DiffuseLight::new_(s, Color::new_(7., 7., 7.));
+    Obj light_rect = XZRect::new_(s, 123., 423., 147., 412., 554., light);
+    world.add(FlipFace::new_(s, light_rect));
+
+    Point3 center1 = Point3::new_(400., 400., 200.);
+    Point3 center2 = center1 + Vec3::new_(25., 0., 0.);
+    Mat moving_sphere_material = Lambertian::new_(s, Color::new_(0.7, 0.3, 0.1));
+    world.add(MovingSphere::new_(s, center1, center2, 0., 1., 50., moving_sphere_material));
+
+    world.add(Sphere::new_(s, Point3::new_(260., 150., 45.), 50., Dielectric::new_(s, 1.5)));
+    world.add(Sphere::new_(s, Point3::new_(0., 150., 145.), 50., Metal::new_(s, Color::new_(0.8, 0.8, 0.9), 1.)));
+
+    // `boundary.clone()`: the visible sphere and the medium's boundary are two copies (by value)
+    Obj boundary = Sphere::new_(s, Point3::new_(360., 150., 145.), 70., Dielectric::new_(s, 1.5));
+    world.add(boundary);
+    Obj boundary_copy = Sphere::new_(s, Point3::new_(360., 150., 145.), 70., Dielectric::new_(s, 1.5));
+    world.add(ConstantMedium::new_(s, boundary_copy, 0.2, Color::new_(0.2, 0.4, 0.9)));
+
+    Obj fog_boundary = Sphere::new_(s, Point3::new_(0., 0., 0.), 5000., Dielectric::new_(s, 1.5));
+    world.add(ConstantMedium::new_(s, fog_boundary, 0.0001, Color::new_(1., 1., 1.)));
+
+    Mat emat = Lambertian::new_arc(s, ImageTexture::new_(s, o.asset_dir + "earthmap.jpg"));
+    world.add(Sphere::new_(s, Point3::new_(400., 200., 400.), 100., emat));
+
+    Tex pertext = NoiseTexture::new_(s, 0.1);
+    world.add(Sphere::new_(s, Point3::new_(220., 280., 300.), 80., Lambertian::new_arc(s, pertext)));
+
+    HittableList box2;
+    Mat white = Lambertian::new_(s, Color::new_(0.73, 0.73, 0.73));
+    const int ns = 1000;
+    for (int i = 0; i < ns; ++i) box2.add(Sphere::new_(s, s.random_vec(0., 165.), 10., white));
+
+    world.add(Translate::new_(s, RotateY::new_(s, BvhNode::new_list(s, box2, 0., 1.), 15.),
+                              Vec3::new_(-100., 270., 395.)));
+
+    // upstream returns the world only; lights as decided in SURVEY.md Q12: the light rect, un-flipped
+    out.lights.add(light_rect);
+    return out;
+}
+
+void get_shuttle(Scene &s, HittableList &world, const SceneOptions &o, double zoom, double angle,
+                 Vec3 offset) { // scene.rs:364-414
+    std::string file_name = o.asset_dir + "obj/Shuttle.obj";
+    std::vector<ObjMesh> models = load_obj(file_name); // assert!(obj.is_ok()) -> throws
+    for (const ObjMesh &m : models) {
+        std::vector<Point3> vertices;
+        for (size_t v = 0; v < m.positions.size() / 3; ++v)
+            vertices.push_back(Point3::new_((double)m.positions[3 * v], (double)m.positions[3 * v + 1],
+                                            (double)m.positions[3 * v + 2]));
+        HittableList object;
+        // upstream builds one Lambertian per triangle (by value); identical materials share one entry
+        Mat mat = Lambertian::new_(s, Color::new_(0.78, 0.78, 0.78));
+        for (size_t v = 0; v < m.indices.size() / 3; ++v) {
+            uint32_t x = m.indices[v * 3], y = m.indices[v * 3 + 1], z = m.indices[v * 3 + 2];
+            object.add(Triangle::new_(s, vertices[x], vertices[y], vertices[z], mat));
+        }
+        Obj obj = BvhNode::new_list(s, object, 0., 1.);
+        obj = Zoom::new_(s, obj, zoom);
+        obj = RotateY::new_(s, obj, angle);
+        obj = Translate::new_(s, obj, offset);
+        world.add(obj);
+    }
+}
+
+// Cornell walls + light (scene.rs:165-196) around the Shuttle mesh; the placement is ours
+// (SURVEY.md 8d, C4): the reference places the shuttle inside wwscene, which cannot load.
+static SceneLists obj_cornell(Scene &s, const SceneOptions &o) {
+    SceneLists out = cornell_box(s);
+    // Shuttle bounds ~[-0.334,-0.0001,-0.475]..[0.335,0.488,0.545]: Zoom(300) makes it ~200 x 146 x 306,
+    // floating in the middle of the 555 room.  Same wrapper order as scene.rs:408-411.
+    get_shuttle(s, out.world, o, 300., 56., Vec3::new_(278., 130., 278.));
+    return out;
+}
+
+// Book-3 final Cornell: tall box + glass sphere, sphere also in `lights`.
+static SceneLists cornell_book3(Scene &s) {
+    SceneLists out = cornell_box(s);
+    Mat white = Lambertian::new_(s, Color::new_(0.73, 0.73, 0.73));
+    Obj box1 = Boxes::new_(s, Point3::new_(0., 0., 0.), Point3::new_(165., 330., 165.), white);
+    box1 = RotateY::new_(s, box1, 15.);
+    box1 = Translate::new_(s, box1, Vec3::new_(265., 0., 295.));
+    out.world.add(box1);
+    Obj glass = Sphere::new_(s, Point3::new_(190., 90., 190.), 90., Dielectric::new_(s, 1.5));
+    out.world.add(glass);
+    out.lights.add(glass);
+    return out;
+}
+
+void build_config(Scene &s, const std::string &name, double aspect_ratio, const SceneOptions &o) {
+    SceneLists l;
+    Vec3 vup = Vec3::new_(0., 1., 0.);
+    if (name == "random_scene") { // C1
+        l = random_scene(s);
+        s.set_camera(Point3::new_(13., 2., 3.), Point3::new_(0., 0., 0.), vup, 20., aspect_ratio, 0.1, 10., 0., 1.);
+        s.background[0] = 0.70; s.background[1] = 0.80; s.background[2] = 1.00;
+    } else if (name == "cornell_box" || name == "cornell_smoke" || name == "cornell_book3") { // C2
+        l = name == "cornell_box" ? cornell_box(s) : (name == "cornell_smoke" ? cornell_smoke(s) : cornell_book3(s));
+        s.set_camera(Point3::new_(278., 278., -800.), Point3::new_(278., 278., 0.), vup, 40., aspect_ratio, 0., 10., 0., 1.);
+    } else if (name == "final_scene") { // C3 / C5
+        l = final_scene(s, o);
+        s.set_camera(Point3::new_(478., 278., -600.), Point3::new_(278., 278., 0.), vup, 40., aspect_ratio, 0., 10., 0., 1.);
+    } else if (name == "obj_cornell") { // C4
+        l = obj_cornell(s, o);
+        s.set_camera(Point3::new_(278., 278., -800.), Point3::new_(278., 278., 0.), vup, 40., aspect_ratio, 0., 10., 0., 1.);
+    } else {
+        throw Error{"unknown scene name: " + name};
+    }
+    // main.rs:90: BvhNode::new_list(&main_world, time0, time1)
+    Obj root = BvhNode::new_list(s, l.world, s.camera.time0, s.camera.time1);
+    s.world = root.id;
+    s.lights.clear();
+    for (Obj li : l.lights.objects) s.lights.push_back(li.id);
+}
+
+} // namespace rt
