@@ -1,0 +1,650 @@
+/*
+ * rt_device.cuh -- device-side restatement of the reference's geometry, materials, textures
+ * and pdfs for sm_100a.  Everything is f64 with the reference's operation order and is
+ * compiled with -fmad=false (rustc never contracts a*b+c), so hit/miss decisions and
+ * primitive ids are bit-identical to BvhNode::hit (hittable/bvh/mod.rs:86-101).
+ *
+ * Layout of the scene in HBM: see include/rtgpu.h.  The traversal program is an array of
+ * 64-byte ops; a thread fetches one op with four 128-bit loads through the read-only path.
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/rt_rng.h"
+#include "../../include/rtgpu.h"
+
+#define RT_NO_HIT 0xffffffffu
+#define RT_MAX_PUSH 4   /* nesting of PUSH ops (instances inside instances) */
+#define RT_MAX_CHAIN 8  /* wrappers around one primitive */
+#define RT_PI 3.14159265358979323846264338327950288
+#define RT_F64_MAX 1.7976931348623157e308
+
+struct V3 {
+    double x, y, z;
+};
+__device__ __forceinline__ V3 v3(double x, double y, double z) { return V3{x, y, z}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 operator-(V3 a) { return V3{-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ V3 operator*(V3 a, V3 b) { return V3{a.x * b.x, a.y * b.y, a.z * b.z}; }
+__device__ __forceinline__ V3 operator*(V3 a, double s) { return V3{a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ V3 operator/(V3 a, double s) { return V3{a.x / s, a.y / s, a.z / s}; }
+__device__ __forceinline__ double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+    return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ double length_sqr(V3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+__device__ __forceinline__ double length(V3 a) { return sqrt(length_sqr(a)); }
+__device__ __forceinline__ V3 to_unit(V3 a) { return a / length(a); }
+
+struct Ray {
+    V3 o, d;
+    double tm;
+};
+__device__ __forceinline__ V3 ray_at(const Ray &r, double t) { return r.o + r.d * t; }
+
+/* device view of a scene (pointers into HBM) */
+struct DScene {
+    const rtgpu_op *ops;
+    const rtgpu_xform *xforms;
+    const uint32_t *chain;
+    const rtgpu_ctx *ctxs;
+    const rtgpu_material *mats;
+    const rtgpu_texture *texs;
+    const rtgpu_perlin *perlins;
+    const rtgpu_image *images;
+    const uint8_t *texels;
+    const rtgpu_light *lights;
+    uint32_t n_ops, n_lights;
+    rtgpu_camera cam;
+    double background[3];
+};
+
+/* ---- 128-bit loads of an op ------------------------------------------------------------- */
+struct OpData {
+    double d[6];
+};
+__device__ __forceinline__ uint4 load_op_header(const rtgpu_op *op) { return __ldg(reinterpret_cast<const uint4 *>(op)); }
+__device__ __forceinline__ void load_op_payload(const rtgpu_op *op, double d[6]) {
+    const double2 *p = reinterpret_cast<const double2 *>(op) + 1;
+    double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y; d[4] = c.x; d[5] = c.y;
+}
+__device__ __forceinline__ void load_slot8(const rtgpu_op *op, double d[8]) { /* second slot of a 2-slot op */
+    const double2 *p = reinterpret_cast<const double2 *>(op);
+    double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), e = __ldg(p + 3);
+    d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y; d[4] = c.x; d[5] = c.y; d[6] = e.x; d[7] = e.y;
+}
+
+/* ---- wrappers: ray into object space (hittable/mod.rs:166,240-248,322) -------------------- */
+__device__ __forceinline__ void xform_ray(const rtgpu_xform &xf, V3 &o, V3 &d) {
+    switch (xf.kind) {
+    case RTGPU_XF_TRANSLATE:
+        o = o - v3(xf.p[0], xf.p[1], xf.p[2]);
+        break;
+    case RTGPU_XF_ROTATE_Y: {
+        double s = xf.p[0], c = xf.p[1];
+        double ox = c * o.x - s * o.z, oz = s * o.x + c * o.z;
+        double dx = c * d.x - s * d.z, dz = s * d.x + c * d.z;
+        o.x = ox; o.z = oz;
+        d.x = dx; d.z = dz;
+        break;
+    }
+    case RTGPU_XF_ZOOM:
+        o = o / xf.p[0]; /* direction left unscaled (Q5) */
+        break;
+    default: /* FLIP: the ray is untouched */
+        break;
+    }
+}
+__device__ __forceinline__ rtgpu_xform load_xform(const DScene &sc, uint32_t chain_idx) {
+    const rtgpu_xform *x = sc.xforms + __ldg(sc.chain + chain_idx);
+    const double2 *p = reinterpret_cast<const double2 *>(x);
+    rtgpu_xform r;
+    double2 a = __ldg(p), b = __ldg(p + 1);
+    uint2 hdr = *reinterpret_cast<uint2 *>(&a.x);
+    r.kind = hdr.x;
+    r.gid = hdr.y;
+    r.p[0] = a.y; r.p[1] = b.x; r.p[2] = b.y;
+    return r;
+}
+
+/* ---- primitive tests: return true and shrink `best` on a hit ------------------------------- */
+/* Sphere::hit, sphere.rs:39-56 (decision part; the record is rebuilt later for the winner) */
+__device__ __forceinline__ bool hit_sphere(V3 o, V3 d, double a, V3 c, double radius, double tmin, double &best) {
+    V3 oc = o - c;
+    double half_b = dot(oc, d);
+    double cc = length_sqr(oc) - radius * radius;
+    double disc = half_b * half_b - a * cc;
+    if (disc < 0.) return false;
+    double sqrtd = sqrt(disc);
+    double root = (-half_b - sqrtd) / a;
+    if (root < tmin || best < root) {
+        root = (-half_b + sqrtd) / a;
+        if (root < tmin || best < root) return false;
+    }
+    best = root;
+    return true;
+}
+/* XYRect/XZRect/YZRect::hit, aarect.rs:46-56,129-139,212-222.  AX = thin axis; (A,B) in-plane.
+ * A NaN t passes the range test, as upstream (Q2). */
+template <int AX>
+__device__ __forceinline__ bool hit_rect(V3 o, V3 d, double a0, double a1, double b0, double b1, double k, double tmin,
+                                         double &best) {
+    double oa, ob, ok, da, db, dk;
+    if (AX == 2) { oa = o.x; ob = o.y; ok = o.z; da = d.x; db = d.y; dk = d.z; }
+    else if (AX == 1) { oa = o.x; ob = o.z; ok = o.y; da = d.x; db = d.z; dk = d.y; }
+    else { oa = o.y; ob = o.z; ok = o.x; da = d.y; db = d.z; dk = d.x; }
+    double t = (k - ok) / dk;
+    if (t < tmin || t > best) return false;
+    double a = oa + t * da;
+    double b = ob + t * db;
+    if (a < a0 || a > a1 || b < b0 || b > b1) return false;
+    best = t;
+    return true;
+}
+/* Boxes::hit = HittableList::hit over six rects (boxes.rs:24-69,82-84; hittable/mod.rs:90-100) */
+__device__ __forceinline__ bool hit_box(V3 o, V3 d, const double p[6], double tmin, double &best, uint32_t &face) {
+    bool any = false;
+    if (hit_rect<2>(o, d, p[0], p[3], p[1], p[4], p[5], tmin, best)) { any = true; face = 0; }
+    if (hit_rect<2>(o, d, p[0], p[3], p[1], p[4], p[2], tmin, best)) { any = true; face = 1; }
+    if (hit_rect<1>(o, d, p[0], p[3], p[2], p[5], p[4], tmin, best)) { any = true; face = 2; }
+    if (hit_rect<1>(o, d, p[0], p[3], p[2], p[5], p[1], tmin, best)) { any = true; face = 3; }
+    if (hit_rect<0>(o, d, p[1], p[4], p[2], p[5], p[3], tmin, best)) { any = true; face = 4; }
+    if (hit_rect<0>(o, d, p[1], p[4], p[2], p[5], p[0], tmin, best)) { any = true; face = 5; }
+    return any;
+}
+/* Triangle::hit, triangle.rs:51-64 with inside() of :33-46; n is get_normal(), precomputed */
+__device__ __forceinline__ bool hit_triangle(V3 o, V3 d, V3 a, V3 b, V3 c, V3 n, double tmin, double &best) {
+    double t = dot(d, n);
+    t = dot(a - o, n) / t;
+    if (t != t || t < tmin || t > best) return false;
+    V3 p = o + d * t;
+    if (!(dot(cross(c - a, p - a), cross(c - a, b - a)) >= 0.)) return false;
+    if (!(dot(cross(a - b, p - b), cross(a - b, c - b)) >= 0.)) return false;
+    if (!(dot(cross(b - c, p - c), cross(b - c, a - c)) >= 0.)) return false;
+    best = t;
+    return true;
+}
+/* AABB::hit, aabb.rs:15-32.  inv = 1/dir is what upstream recomputes per node; one final
+ * `t_max <= t_min` test is equivalent to the per-axis early exits (bounds are monotone). */
+__device__ __forceinline__ bool hit_aabb(V3 o, V3 inv, const double b[6], double tmin, double tmax) {
+    double t0 = (b[0] - o.x) * inv.x, t1 = (b[3] - o.x) * inv.x;
+    if (inv.x < 0.) { double s = t0; t0 = t1; t1 = s; }
+    tmin = t0 > tmin ? t0 : tmin;
+    tmax = t1 < tmax ? t1 : tmax;
+    if (tmax <= tmin) return false;
+    t0 = (b[1] - o.y) * inv.y; t1 = (b[4] - o.y) * inv.y;
+    if (inv.y < 0.) { double s = t0; t0 = t1; t1 = s; }
+    tmin = t0 > tmin ? t0 : tmin;
+    tmax = t1 < tmax ? t1 : tmax;
+    if (tmax <= tmin) return false;
+    t0 = (b[2] - o.z) * inv.z; t1 = (b[5] - o.z) * inv.z;
+    if (inv.z < 0.) { double s = t0; t0 = t1; t1 = s; }
+    tmin = t0 > tmin ? t0 : tmin;
+    tmax = t1 < tmax ? t1 : tmax;
+    return !(tmax <= tmin);
+}
+
+/* ---- closest hit over a program range ------------------------------------------------------ */
+struct Closest {
+    double t;      /* running best (= t_max when nothing was hit) */
+    uint32_t op;   /* index of the winning op, RT_NO_HIT if none */
+    uint32_t face; /* box side of the winner */
+};
+
+/* Walks ops [begin, end) in order -- the reference's left-then-right recursion unrolled
+ * (SURVEY.md 2.5).  MAIN = false is the boundary walk of a ConstantMedium (no nested media,
+ * no rng).  `rng` draws the medium's free path (constantmedium.rs:60) in visiting order. */
+template <bool MAIN>
+__device__ __noinline__ Closest closest_hit(const DScene &sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm,
+                                            double tmin, double tmax, rt_rng *rng) {
+    Closest best;
+    best.t = tmax;
+    best.op = RT_NO_HIT;
+    best.face = 0;
+    V3 inv = v3(1. / d.x, 1. / d.y, 1. / d.z);
+    double a = length_sqr(d);
+    V3 saved_o[RT_MAX_PUSH], saved_d[RT_MAX_PUSH];
+    int sp = 0;
+    uint32_t i = begin;
+    while (i < end) {
+        const rtgpu_op *op = sc.ops + i;
+        uint4 h = load_op_header(op);
+        uint32_t kind = h.x & 0xffu;
+        double p[6];
+        if (kind != RTGPU_OP_POP) load_op_payload(op, p);
+        switch (kind) {
+        case RTGPU_OP_NODE:
+            i = hit_aabb(o, inv, p, tmin, best.t) ? i + 1 : h.y;
+            break;
+        case RTGPU_OP_SPHERE:
+            if (hit_sphere(o, d, a, v3(p[0], p[1], p[2]), p[3], tmin, best.t)) best.op = i;
+            i += 1;
+            break;
+        case RTGPU_OP_MSPHERE: {
+            double q[8];
+            load_slot8(op + 1, q);
+            /* MovingSphere::center, sphere.rs:124-127 */
+            V3 c0 = v3(p[0], p[1], p[2]), c1 = v3(q[0], q[1], q[2]);
+            V3 c = c0 + (c1 - c0) * ((tm - p[4]) / (p[5] - p[4]));
+            if (hit_sphere(o, d, a, c, p[3], tmin, best.t)) best.op = i;
+            i += 2;
+            break;
+        }
+        case RTGPU_OP_RECT_XY:
+            if (hit_rect<2>(o, d, p[0], p[1], p[2], p[3], p[4], tmin, best.t)) best.op = i;
+            i += 1;
+            break;
+        case RTGPU_OP_RECT_XZ:
+            if (hit_rect<1>(o, d, p[0], p[1], p[2], p[3], p[4], tmin, best.t)) best.op = i;
+            i += 1;
+            break;
+        case RTGPU_OP_RECT_YZ:
+            if (hit_rect<0>(o, d, p[0], p[1], p[2], p[3], p[4], tmin, best.t)) best.op = i;
+            i += 1;
+            break;
+        case RTGPU_OP_BOX:
+            if (hit_box(o, d, p, tmin, best.t, best.face)) best.op = i;
+            i += 1;
+            break;
+        case RTGPU_OP_TRI: {
+            double q[8];
+            load_slot8(op + 1, q);
+            if (hit_triangle(o, d, v3(p[0], p[1], p[2]), v3(p[3], p[4], p[5]), v3(q[0], q[1], q[2]), v3(q[3], q[4], q[5]),
+                             tmin, best.t))
+                best.op = i;
+            i += 2;
+            break;
+        }
+        case RTGPU_OP_MEDIUM:
+            if (MAIN) { /* ConstantMedium::hit, constantmedium.rs:49-83 */
+                Closest r1 = closest_hit<false>(sc, i + 1, h.y, o, d, tm, -CUDART_INF, CUDART_INF, nullptr);
+                if (r1.op != RT_NO_HIT) {
+                    Closest r2 = closest_hit<false>(sc, i + 1, h.y, o, d, tm, r1.t + 0.0001, CUDART_INF, nullptr);
+                    if (r2.op != RT_NO_HIT) {
+                        double t1 = fmax(r1.t, tmin);
+                        double t2 = fmin(r2.t, best.t);
+                        if (!(t1 >= t2)) {
+                            t1 = fmax(t1, 0.);
+                            double ray_length = sqrt(a);
+                            double distance_inside_boundary = (t2 - t1) * ray_length;
+                            double rnd = rng->gen();
+                            double hit_distance = p[0] * log(rnd); /* neg_inv_density * rnd.log(E) */
+                            if (!(hit_distance > distance_inside_boundary)) {
+                                best.t = t1 + hit_distance / ray_length;
+                                best.op = i;
+                            }
+                        }
+                    }
+                }
+            }
+            i = h.y;
+            break;
+        case RTGPU_OP_PUSH: {
+            saved_o[sp] = o;
+            saved_d[sp] = d;
+            ++sp;
+            for (uint32_t j = 0; j < h.w; ++j) {
+                rtgpu_xform xf = load_xform(sc, h.z + j);
+                xform_ray(xf, o, d);
+            }
+            inv = v3(1. / d.x, 1. / d.y, 1. / d.z);
+            a = length_sqr(d);
+            i += 1;
+            break;
+        }
+        default: /* POP */
+            --sp;
+            o = saved_o[sp];
+            d = saved_d[sp];
+            inv = v3(1. / d.x, 1. / d.y, 1. / d.z);
+            a = length_sqr(d);
+            i += 1;
+            break;
+        }
+    }
+    return best;
+}
+
+/* ---- HitRecord of the winner (hittable/mod.rs:18-57), rebuilt once per ray ------------------- */
+struct HitRec {
+    V3 p, n;
+    double t, u, v;
+    bool front;
+    uint32_t mat;
+    int32_t gid, face, inst;
+};
+__device__ __forceinline__ void set_face_normal(HitRec &rec, V3 rdir, V3 outward) { /* hittable/mod.rs:49-56 */
+    rec.front = dot(rdir, outward) < 0.;
+    rec.n = rec.front ? outward : -outward;
+}
+__device__ __forceinline__ void sphere_uv(V3 p, double &u, double &v) { /* sphere.rs:30-34 */
+    double theta = acos(-p.y);
+    double phi = atan2(-p.z, p.x) + RT_PI;
+    u = phi / (2. * RT_PI);
+    v = theta / RT_PI;
+}
+template <int AX>
+__device__ __forceinline__ void rect_record(HitRec &rec, V3 o, V3 d, double a0, double a1, double b0, double b1, double t) {
+    double oa, ob, da, db;
+    if (AX == 2) { oa = o.x; ob = o.y; da = d.x; db = d.y; }
+    else if (AX == 1) { oa = o.x; ob = o.z; da = d.x; db = d.z; }
+    else { oa = o.y; ob = o.z; da = d.y; db = d.z; }
+    double a = oa + t * da;
+    double b = ob + t * db;
+    rec.u = (a - a0) / (a1 - a0);
+    rec.v = (b - b0) / (b1 - b0);
+    rec.p = o + d * t;
+    set_face_normal(rec, d, v3(AX == 0 ? 1. : 0., AX == 1 ? 1. : 0., AX == 2 ? 1. : 0.));
+}
+
+__device__ __noinline__ void make_record(const DScene &sc, const Ray &wr, double t, uint32_t opi, uint32_t face, HitRec &rec) {
+    const rtgpu_op *op = sc.ops + opi;
+    uint4 h = load_op_header(op);
+    uint32_t kind = h.x & 0xffu;
+    double p[6];
+    load_op_payload(op, p);
+    rtgpu_ctx ctx = sc.ctxs[h.x >> 8];
+    /* outermost wrapper first: the ray each wrapper hands to its child */
+    V3 o = wr.o, d = wr.d;
+    V3 dirs[RT_MAX_CHAIN];
+    for (uint32_t j = 0; j < ctx.len; ++j) {
+        rtgpu_xform xf = load_xform(sc, ctx.start + j);
+        xform_ray(xf, o, d);
+        dirs[j] = d;
+    }
+    rec.t = t;
+    rec.mat = h.z;
+    rec.gid = (int32_t)h.w;
+    rec.face = 0;
+    rec.inst = -1;
+    switch (kind) {
+    case RTGPU_OP_SPHERE:
+    case RTGPU_OP_MSPHERE: { /* sphere.rs:58-64,157-163 */
+        V3 c = v3(p[0], p[1], p[2]);
+        if (kind == RTGPU_OP_MSPHERE) {
+            double q[8];
+            load_slot8(op + 1, q);
+            c = c + (v3(q[0], q[1], q[2]) - c) * ((wr.tm - p[4]) / (p[5] - p[4]));
+        }
+        V3 at = o + d * t;
+        V3 outward = (at - c) / p[3];
+        sphere_uv(outward, rec.u, rec.v);
+        rec.p = at;
+        set_face_normal(rec, d, outward);
+        break;
+    }
+    case RTGPU_OP_RECT_XY: rect_record<2>(rec, o, d, p[0], p[1], p[2], p[3], t); break;
+    case RTGPU_OP_RECT_XZ: rect_record<1>(rec, o, d, p[0], p[1], p[2], p[3], t); break;
+    case RTGPU_OP_RECT_YZ: rect_record<0>(rec, o, d, p[0], p[1], p[2], p[3], t); break;
+    case RTGPU_OP_BOX:
+        rec.face = (int32_t)face;
+        switch (face) { /* boxes.rs:24-69 */
+        case 0: case 1: rect_record<2>(rec, o, d, p[0], p[3], p[1], p[4], t); break;
+        case 2: case 3: rect_record<1>(rec, o, d, p[0], p[3], p[2], p[5], t); break;
+        default: rect_record<0>(rec, o, d, p[1], p[4], p[2], p[5], t); break;
+        }
+        break;
+    case RTGPU_OP_TRI: { /* triangle.rs:62-76 */
+        double q[8];
+        load_slot8(op + 1, q);
+        V3 a = v3(p[0], p[1], p[2]), b = v3(p[3], p[4], p[5]), c = v3(q[0], q[1], q[2]), n = v3(q[3], q[4], q[5]);
+        V3 pt = o + d * t;
+        double a1 = a.x - b.x, b1 = a.x - c.x, c1 = a.x - pt.x;
+        double a2 = a.y - b.y, b2 = a.y - c.y, c2 = a.y - pt.y;
+        rec.u = (c1 * b2 - b1 * c2) / (a1 * b2 - b1 * a2);
+        rec.v = (a1 * c2 - a2 * c1) / (a1 * b2 - b1 * a2);
+        rec.p = pt;
+        set_face_normal(rec, d, n);
+        break;
+    }
+    default: /* MEDIUM, constantmedium.rs:70-78 */
+        rec.p = o + d * t;
+        rec.n = v3(1., 0., 0.);
+        rec.u = 0.;
+        rec.v = 0.;
+        rec.front = true;
+        break;
+    }
+    /* innermost wrapper first: record back to world space (hittable/mod.rs:167-171,250-261,283-285,323-327) */
+    for (int j = (int)ctx.len - 1; j >= 0; --j) {
+        rtgpu_xform xf = load_xform(sc, ctx.start + (uint32_t)j);
+        if (rec.inst < 0) rec.inst = (int32_t)xf.gid;
+        switch (xf.kind) {
+        case RTGPU_XF_TRANSLATE:
+            rec.p = rec.p + v3(xf.p[0], xf.p[1], xf.p[2]);
+            set_face_normal(rec, dirs[j], rec.n);
+            break;
+        case RTGPU_XF_ROTATE_Y: {
+            double s = xf.p[0], c = xf.p[1];
+            V3 pp = rec.p, nn = rec.n;
+            pp.x = c * rec.p.x + s * rec.p.z;
+            pp.z = -s * rec.p.x + c * rec.p.z;
+            nn.x = c * rec.n.x + s * rec.n.z;
+            nn.z = -s * rec.n.x + c * rec.n.z;
+            rec.p = pp;
+            set_face_normal(rec, dirs[j], nn); /* object-space ray vs world-space normal (Q4) */
+            break;
+        }
+        case RTGPU_XF_ZOOM:
+            rec.p = rec.p * xf.p[0];
+            set_face_normal(rec, dirs[j], rec.n);
+            break;
+        default:
+            rec.front = !rec.front;
+            break;
+        }
+    }
+}
+
+/* ---- textures (texture/mod.rs, texture/perlin.rs) ------------------------------------------ */
+__device__ __forceinline__ int32_t floor_i32(double f) { /* `as i32`: saturating, NaN -> 0 */
+    double fl = floor(f);
+    if (fl != fl) return 0;
+    if (fl >= 2147483647.0) return 2147483647;
+    if (fl <= -2147483648.0) return (int32_t)0x80000000;
+    return (int32_t)fl;
+}
+__device__ double perlin_noise(const rtgpu_perlin &t, V3 p) { /* perlin.rs:52-99 (double smoothing, Q9) */
+    double u = p.x - floor(p.x), v = p.y - floor(p.y), w = p.z - floor(p.z);
+    u = u * u * (3. - 2. * u);
+    v = v * v * (3. - 2. * v);
+    w = w * w * (3. - 2. * w);
+    int32_t i = floor_i32(p.x), j = floor_i32(p.y), k = floor_i32(p.z);
+    double uu = u * u * (3. - 2. * u), vv = v * v * (3. - 2. * v), ww = w * w * (3. - 2. * w);
+    double accum = 0.;
+#pragma unroll
+    for (int di = 0; di < 2; ++di)
+#pragma unroll
+        for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+            for (int dk = 0; dk < 2; ++dk) {
+                int idx = __ldg(&t.perm_x[(uint32_t)(i + di) & 255]) ^ __ldg(&t.perm_y[(uint32_t)(j + dj) & 255]) ^
+                          __ldg(&t.perm_z[(uint32_t)(k + dk) & 255]);
+                V3 c = v3(__ldg(&t.randvec[idx][0]), __ldg(&t.randvec[idx][1]), __ldg(&t.randvec[idx][2]));
+                V3 weight_v = v3(u - (double)di, v - (double)dj, w - (double)dk);
+                accum += dot(c, weight_v) * ((double)di * uu + (double)(1 - di) * (1. - uu)) *
+                         ((double)dj * vv + (double)(1 - dj) * (1. - vv)) * ((double)dk * ww + (double)(1 - dk) * (1. - ww));
+            }
+    return accum;
+}
+__device__ double perlin_turb(const rtgpu_perlin &t, V3 p, int depth) { /* perlin.rs:100-112 */
+    double accum = 0., weight = 1.;
+    V3 tmp = p;
+    for (int i = 0; i < depth; ++i) {
+        accum += weight * perlin_noise(t, tmp);
+        weight *= 0.5;
+        tmp = tmp * 2.;
+    }
+    return fabs(accum);
+}
+__device__ V3 texture_value(const DScene &sc, uint32_t id, double u, double v, V3 p) {
+    for (int depth = 0; depth < 16; ++depth) {
+        const rtgpu_texture &t = sc.texs[id];
+        switch (t.kind) {
+        case 0: /* SolidColor, texture/mod.rs:25-29 */
+            return v3(t.p[0], t.p[1], t.p[2]);
+        case 1: { /* CheckerTexture, texture/mod.rs:52-59 */
+            double sines = sin(p.x * 10.) * sin(p.y * 10.) * sin(p.z * 10.);
+            id = (uint32_t)(sines < 0. ? t.a : t.b);
+            break;
+        }
+        case 2: { /* NoiseTexture, texture/mod.rs:75-79 */
+            double s = 0.5 * (1. + sin(t.p[0] * p.z + 10. * perlin_turb(sc.perlins[t.a], p, 7)));
+            return v3(1. * s, 1. * s, 1. * s); /* Color(1,1,1) * 0.5 * (...) = ((1*0.5) * (...)) per channel */
+        }
+        default: { /* ImageTexture, texture/mod.rs:110-138 */
+            if (t.a < 0) return v3(0., 1., 1.);
+            const rtgpu_image &im = sc.images[t.a];
+            if (u < 0.) u = 0.;
+            if (u > 1.) u = 1.; /* f64::clamp keeps NaN */
+            if (v < 0.) v = 0.;
+            if (v > 1.) v = 1.;
+            double fi = u * (double)im.width, fj = v * (double)im.height;
+            long long i = (fi > 0.) ? (fi >= 9.2e18 ? 0x7fffffffffffffffLL : (long long)fi) : 0; /* `as usize` */
+            long long j = (fj > 0.) ? (fj >= 9.2e18 ? 0x7fffffffffffffffLL : (long long)fj) : 0;
+            if (i >= im.width) i = im.width - 1;
+            if (j >= im.height) j = im.height - 1;
+            const double color_scale = 1. / 255.999;
+            const uint8_t *px = sc.texels + im.offset + 3 * (j * (long long)im.width + i);
+            return v3((double)__ldg(px) * color_scale, (double)__ldg(px + 1) * color_scale, (double)__ldg(px + 2) * color_scale);
+        }
+        }
+    }
+    return v3(0., 0., 0.);
+}
+
+/* ---- random helpers (basic/vec.rs, basic/pdf.rs) --------------------------------------------- */
+__device__ __forceinline__ V3 random_in_unit_sphere(rt_rng &rng) { /* vec.rs:69-76 */
+    for (;;) {
+        double x = rng.gen_range(-1., 1.);
+        double y = rng.gen_range(-1., 1.);
+        double z = rng.gen_range(-1., 1.);
+        V3 p = v3(x, y, z);
+        if (length(p) < 1.) return p;
+    }
+}
+__device__ __forceinline__ V3 random_in_unit_disk(rt_rng &rng) { /* vec.rs:88-96 */
+    for (;;) {
+        double x = rng.gen_range(-1.0, 1.0);
+        double y = rng.gen_range(-1.0, 1.0);
+        V3 p = v3(x, y, 0.);
+        if (length(p) < 1.) return p;
+    }
+}
+__device__ __forceinline__ V3 random_cosine_direction(rt_rng &rng) { /* pdf.rs:12-21 */
+    double r1 = rng.gen();
+    double r2 = rng.gen();
+    double z = sqrt(1. - r2);
+    double phi = 2. * RT_PI * r1;
+    double x = cos(phi) * sqrt(r2);
+    double y = sin(phi) * sqrt(r2);
+    return v3(x, y, z);
+}
+__device__ __forceinline__ V3 random_to_sphere(rt_rng &rng, double radius, double dis_sqr) { /* vec.rs:108-117 */
+    double r1 = rng.gen();
+    double r2 = rng.gen();
+    double z = 1. + r2 * (sqrt(1. - radius * radius / dis_sqr) - 1.);
+    double phi = 2. * RT_PI * r1;
+    double x = cos(phi) * sqrt(1. - z * z);
+    double y = sin(phi) * sqrt(1. - z * z);
+    return v3(x, y, z);
+}
+struct Onb {
+    V3 u, v, w;
+};
+__device__ __forceinline__ Onb onb_from_w(V3 n) { /* onb.rs:26-35 */
+    Onb o;
+    o.w = to_unit(n);
+    V3 a = fabs(o.w.x) > 0.9 ? v3(0., 1., 0.) : v3(1., 0., 0.);
+    o.v = to_unit(cross(o.w, a));
+    o.u = cross(o.w, o.v);
+    return o;
+}
+__device__ __forceinline__ V3 onb_local(const Onb &o, V3 a) { return o.u * a.x + o.v * a.y + o.w * a.z; } /* onb.rs:22-24 */
+__device__ __forceinline__ V3 reflect(V3 v, V3 n) { return v - n * dot(v, n) * 2.; } /* vec.rs:119-121 */
+__device__ __forceinline__ V3 refract(V3 uv, V3 n, double etai_over_etat) { /* vec.rs:123-128 */
+    double cos_theta = fmin(dot(-uv, n), 1.);
+    V3 r_out_perp = (uv + n * cos_theta) * etai_over_etat;
+    V3 r_out_parallel = -n * sqrt(fabs(1. - length_sqr(r_out_perp)));
+    return r_out_perp + r_out_parallel;
+}
+__device__ __forceinline__ double reflectance(double cosv, double ref_idx) { /* material/mod.rs:112-116 */
+    double r0 = (1. - ref_idx) / (1. + ref_idx);
+    r0 = r0 * r0;
+    double x = 1. - cosv;
+    double x2 = x * x;
+    double x4 = x2 * x2;
+    return r0 + (1. - r0) * (x * x4); /* powi(5) as compiler-rt's __powidf2 evaluates it */
+}
+
+/* ---- lights: HittableList::{random, pdf_value} over the lowered `lights` (hittable/mod.rs:121-132) */
+template <int AX>
+__device__ __forceinline__ double rect_pdf_value(const rtgpu_light &l, V3 o, V3 v) { /* aarect.rs:74-83,157-166,240-249 */
+    double best = CUDART_INF;
+    if (!hit_rect<AX>(o, v, l.p[0], l.p[1], l.p[2], l.p[3], l.p[4], 0.001, best)) return 0.;
+    double area = (l.p[1] - l.p[0]) * (l.p[3] - l.p[2]);
+    double dis_sqr = best * best * length_sqr(v);
+    V3 outward = v3(AX == 0 ? 1. : 0., AX == 1 ? 1. : 0., AX == 2 ? 1. : 0.);
+    V3 n = dot(v, outward) < 0. ? outward : -outward;
+    double cosv = fabs(dot(v, n) / length(v));
+    return dis_sqr / (cosv * area);
+}
+__device__ double lights_pdf_value(const DScene &sc, V3 o, V3 v) {
+    double sum = 0.;
+    for (uint32_t i = 0; i < sc.n_lights; ++i) {
+        const rtgpu_light &l = sc.lights[i];
+        double pv = 0.;
+        switch (l.kind) {
+        case RTGPU_LIGHT_RECT_XY: pv = rect_pdf_value<2>(l, o, v); break;
+        case RTGPU_LIGHT_RECT_XZ: pv = rect_pdf_value<1>(l, o, v); break;
+        case RTGPU_LIGHT_RECT_YZ: pv = rect_pdf_value<0>(l, o, v); break;
+        case RTGPU_LIGHT_SPHERE: { /* sphere.rs:75-83 */
+            V3 c = v3(l.p[0], l.p[1], l.p[2]);
+            double best = CUDART_INF;
+            if (hit_sphere(o, v, length_sqr(v), c, l.p[3], 0.001, best)) {
+                double cos_max = sqrt(1. - l.p[3] * l.p[3] / length_sqr(c - o));
+                double solid_angle = 2. * RT_PI * (1. - cos_max);
+                pv = 1. / solid_angle;
+            }
+            break;
+        }
+        default: pv = 0.; break; /* trait default, hittable/mod.rs:62-64 */
+        }
+        sum += pv;
+    }
+    return sum / (double)sc.n_lights;
+}
+__device__ V3 lights_random(const DScene &sc, V3 o, rt_rng &rng) {
+    uint32_t target = rng.gen_index(sc.n_lights);
+    const rtgpu_light &l = sc.lights[target];
+    switch (l.kind) {
+    case RTGPU_LIGHT_RECT_XY: { /* aarect.rs:85-93 */
+        double a = rng.gen_range(l.p[0], l.p[1]);
+        double b = rng.gen_range(l.p[2], l.p[3]);
+        return v3(a, b, l.p[4]) - o;
+    }
+    case RTGPU_LIGHT_RECT_XZ: { /* aarect.rs:168-176 */
+        double a = rng.gen_range(l.p[0], l.p[1]);
+        double b = rng.gen_range(l.p[2], l.p[3]);
+        return v3(a, l.p[4], b) - o;
+    }
+    case RTGPU_LIGHT_RECT_YZ: { /* aarect.rs:251-259 */
+        double a = rng.gen_range(l.p[0], l.p[1]);
+        double b = rng.gen_range(l.p[2], l.p[3]);
+        return v3(l.p[4], a, b) - o;
+    }
+    case RTGPU_LIGHT_SPHERE: { /* sphere.rs:85-90 */
+        V3 direction = v3(l.p[0], l.p[1], l.p[2]) - o;
+        double dis_sqr = length_sqr(direction);
+        Onb uvw = onb_from_w(direction);
+        return onb_local(uvw, random_to_sphere(rng, l.p[3], dis_sqr));
+    }
+    default:
+        return v3(1., 0., 0.); /* trait default, hittable/mod.rs:65-67 */
+    }
+}

@@ -1,0 +1,832 @@
+/*
+ * rt_kernels.cu -- wavefront path tracer for sm_100a and the C ABI of include/rtgpu.h.
+ *
+ * One wave = S samples of every pixel, all in flight at once (paths = S * W * H).  Per bounce:
+ *
+ *   k_extend   closest hit of every live ray against the flat traversal program
+ *              (BvhNode::hit, hittable/bvh/mod.rs:86-101, unrolled -- rt_device.cuh)
+ *   k_shade    HitRecord of the winner, emitted/scatter/MixturePdf (ray_color, main.rs:233-278),
+ *              survivors appended to the next queue with one warp-aggregated atomic
+ *              (ballot + popc prefix) -- the compaction between bounces
+ *
+ * Path state lives in SoA queues of doubles (coalesced 8-byte lanes); the queue length stays on
+ * the device (k_extend/k_shade of bounce b read counts[b], k_shade bumps counts[b+1]), so a
+ * whole wave is enqueued without a host round trip.  Every path writes its radiance exactly
+ * once, to contrib[path id], when it ends (miss / light / absorbed); k_accumulate then sums the
+ * S samples of a pixel in a fixed order, which makes the image independent of scheduling.
+ * Randomness: one Philox slot stream per path, keyed (seed, pixel, sample) -- include/rt_rng.h.
+ */
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "rt_device.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+#define CK(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess) {                                                                                   \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                                            \
+            return e_ == cudaErrorMemoryAllocation ? RTGPU_ERR_OOM : RTGPU_ERR_CUDA;                               \
+        }                                                                                                          \
+    } while (0)
+
+constexpr int kThreads = 128;
+constexpr int kSMs = 148;
+constexpr int kBlocksPerSM = 8;
+
+struct PathQueue { /* SoA, one slot per live path */
+    double *ox, *oy, *oz, *dx, *dy, *dz, *tm; /* ray */
+    double *bx, *by, *bz;                      /* throughput */
+    uint32_t *pid;                             /* path id inside the wave */
+    uint32_t *rng;                             /* next slot of the path's Philox stream */
+};
+struct HitBuf {
+    double *t;
+    uint32_t *op; /* op index | box face << 29; RT_NO_HIT = miss */
+};
+struct WaveParams {
+    uint64_t seed;
+    uint32_t first_pixel, npix_wave, sample_begin, n_paths;
+    int32_t width, height;
+};
+
+__device__ __forceinline__ void path_rng(rt_rng &rng, const WaveParams &wp, uint32_t pid, uint32_t pos) {
+    uint32_t pixel = wp.first_pixel + pid % wp.npix_wave;
+    uint32_t sample = wp.sample_begin + pid / wp.npix_wave;
+    rng.init(wp.seed, pixel, sample, RT_DOMAIN_PATH, pos);
+}
+
+/* main.rs:145-149 + Camera::get_ray, camera.rs:64-73 */
+__device__ __forceinline__ Ray camera_ray(const rtgpu_camera &cam, int x, int y, int w, int h, rt_rng &rng) {
+    double rand_u = rng.gen();
+    double rand_v = rng.gen();
+    double s = ((double)x + rand_u) / (double)(w - 1);
+    double t = ((double)y + rand_v) / (double)(h - 1);
+    V3 cu = v3(cam.u[0], cam.u[1], cam.u[2]), cv = v3(cam.v[0], cam.v[1], cam.v[2]);
+    V3 origin = v3(cam.origin[0], cam.origin[1], cam.origin[2]);
+    V3 llc = v3(cam.lower_left_corner[0], cam.lower_left_corner[1], cam.lower_left_corner[2]);
+    V3 horizontal = v3(cam.horizontal[0], cam.horizontal[1], cam.horizontal[2]);
+    V3 vertical = v3(cam.vertical[0], cam.vertical[1], cam.vertical[2]);
+    V3 rd = random_in_unit_disk(rng) * cam.lens_radius; /* sampled even when the aperture is 0 */
+    V3 offset = cu * rd.x + cv * rd.y;
+    Ray r;
+    r.o = origin + offset;
+    r.d = llc + horizontal * s + vertical * t - origin - offset;
+    r.tm = rng.gen_range(cam.time0, cam.time1);
+    return r;
+}
+
+__global__ void __launch_bounds__(kThreads) k_raygen(DScene sc, PathQueue q, WaveParams wp) {
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x; pid < wp.n_paths; pid += stride) {
+        uint32_t pixel = wp.first_pixel + pid % wp.npix_wave;
+        rt_rng rng;
+        path_rng(rng, wp, pid, 0);
+        Ray r = camera_ray(sc.cam, (int)(pixel % (uint32_t)wp.width), (int)(pixel / (uint32_t)wp.width), wp.width, wp.height, rng);
+        q.ox[pid] = r.o.x; q.oy[pid] = r.o.y; q.oz[pid] = r.o.z;
+        q.dx[pid] = r.d.x; q.dy[pid] = r.d.y; q.dz[pid] = r.d.z;
+        q.tm[pid] = r.tm;
+        q.bx[pid] = 1.; q.by[pid] = 1.; q.bz[pid] = 1.;
+        q.pid[pid] = pid;
+        q.rng[pid] = rng.pos;
+    }
+}
+
+/* world.hit(r, 0.001, f64::MAX), main.rs:243 */
+__global__ void __launch_bounds__(kThreads) k_extend(DScene sc, PathQueue q, HitBuf hb, const uint32_t *count, WaveParams wp) {
+    uint32_t n = *count;
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        V3 o = v3(q.ox[i], q.oy[i], q.oz[i]);
+        V3 d = v3(q.dx[i], q.dy[i], q.dz[i]);
+        rt_rng rng;
+        path_rng(rng, wp, q.pid[i], q.rng[i]);
+        Closest c = closest_hit<true>(sc, 0, sc.n_ops, o, d, q.tm[i], 0.001, RT_F64_MAX, &rng);
+        hb.t[i] = c.t;
+        hb.op[i] = c.op == RT_NO_HIT ? RT_NO_HIT : (c.op | (c.face << 29));
+        q.rng[i] = rng.pos;
+    }
+}
+
+/* the body of ray_color (main.rs:233-278) for one segment; returns true when the path goes on */
+__device__ __forceinline__ bool shade_segment(const DScene &sc, const Ray &r, double t, uint32_t hop, rt_rng &rng,
+                                              V3 &beta, Ray &next, V3 &contrib) {
+    if (hop == RT_NO_HIT) { /* main.rs:275-277 */
+        contrib = beta * v3(sc.background[0], sc.background[1], sc.background[2]);
+        return false;
+    }
+    HitRec rec;
+    make_record(sc, r, t, hop & 0x1fffffffu, hop >> 29, rec);
+    const rtgpu_material &m = sc.mats[rec.mat];
+    switch (m.kind) {
+    case 3: { /* DiffuseLight: emitted, no scatter (material/mod.rs:173-181; main.rs:272-274) */
+        V3 e = rec.front ? texture_value(sc, m.tex, rec.u, rec.v, rec.p) : v3(0., 0., 0.);
+        contrib = beta * e;
+        return false;
+    }
+    case 1: { /* Metal, material/mod.rs:85-96: time reset to 0, no absorption test (Q6) */
+        V3 reflected = reflect(to_unit(r.d), rec.n);
+        next.o = rec.p;
+        next.d = reflected + random_in_unit_sphere(rng) * m.p[3];
+        next.tm = 0.;
+        beta = beta * v3(m.p[0], m.p[1], m.p[2]);
+        return true;
+    }
+    case 2: { /* Dielectric, material/mod.rs:120-147 */
+        double refraction_ratio = rec.front ? 1. / m.p[0] : m.p[0];
+        V3 unit_direction = to_unit(r.d);
+        double cos_theta = fmin(dot(-unit_direction, rec.n), 1.);
+        double sin_theta = sqrt(1. - cos_theta * cos_theta);
+        bool cannot_refract = refraction_ratio * sin_theta > 1.;
+        double random_double = rng.gen_range(0.0, 1.0);
+        V3 direction = (cannot_refract || reflectance(cos_theta, refraction_ratio) > random_double)
+                           ? reflect(unit_direction, rec.n)
+                           : refract(unit_direction, rec.n, refraction_ratio);
+        next.o = rec.p;
+        next.d = direction;
+        next.tm = r.tm;
+        return true; /* attenuation (1,1,1) */
+    }
+    case 4: { /* Isotropic, material/mod.rs:206-214 */
+        next.o = rec.p;
+        next.d = random_in_unit_sphere(rng);
+        next.tm = r.tm;
+        beta = beta * texture_value(sc, m.tex, rec.u, rec.v, rec.p);
+        return true;
+    }
+    default: { /* Lambertian + MixturePdf(HittablePdf(lights), CosPdf), main.rs:263-271 */
+        V3 attenuation = texture_value(sc, m.tex, rec.u, rec.v, rec.p);
+        Onb uvw = onb_from_w(rec.n); /* CosPdf::new(rec.normal), pdf.rs:35-39 */
+        V3 direction;
+        double pdf_val;
+        if (sc.n_lights == 0) {
+            /* Q12: empty `lights` -> the cosine pdf alone (decision shared with the oracle) */
+            direction = onb_local(uvw, random_cosine_direction(rng));
+            double c = dot(to_unit(direction), uvw.w);
+            pdf_val = c <= 0. ? 0. : c / RT_PI;
+        } else {
+            if (rng.gen_range(0.0, 1.0) < 0.5) /* MixturePdf::generate, pdf.rs:95-101 */
+                direction = lights_random(sc, rec.p, rng);
+            else
+                direction = onb_local(uvw, random_cosine_direction(rng));
+            double c = dot(to_unit(direction), uvw.w);
+            double cos_pdf = c <= 0. ? 0. : c / RT_PI;                            /* CosPdf::value, pdf.rs:46-53 */
+            pdf_val = 0.5 * lights_pdf_value(sc, rec.p, direction) + 0.5 * cos_pdf; /* pdf.rs:102-104 */
+        }
+        double cosine = dot(rec.n, to_unit(direction)); /* Lambertian::scattering_pdf, material/mod.rs:58-65 */
+        double spdf = cosine < 0. ? 0. : cosine / RT_PI;
+        next.o = rec.p;
+        next.d = direction;
+        next.tm = r.tm;
+        beta = beta * (attenuation * spdf / pdf_val); /* no pdf == 0 guard upstream either (Q10) */
+        return true;
+    }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_shade(DScene sc, PathQueue qin, HitBuf hb, PathQueue qout, const uint32_t *count_in,
+                                                    uint32_t *count_out, double *cx, double *cy, double *cz, uint32_t *path_len,
+                                                    WaveParams wp, uint32_t bounce) {
+    uint32_t n = *count_in;
+    uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < n; i0 += stride) {
+        uint32_t i = i0 + lane;
+        bool alive = false;
+        Ray next;
+        V3 beta;
+        uint32_t pid = 0, pos = 0;
+        if (i < n) {
+            Ray r;
+            r.o = v3(qin.ox[i], qin.oy[i], qin.oz[i]);
+            r.d = v3(qin.dx[i], qin.dy[i], qin.dz[i]);
+            r.tm = qin.tm[i];
+            beta = v3(qin.bx[i], qin.by[i], qin.bz[i]);
+            pid = qin.pid[i];
+            rt_rng rng;
+            path_rng(rng, wp, pid, qin.rng[i]);
+            V3 contrib;
+            alive = shade_segment(sc, r, hb.t[i], hb.op[i], rng, beta, next, contrib);
+            pos = rng.pos;
+            if (!alive) {
+                cx[pid] = contrib.x;
+                cy[pid] = contrib.y;
+                cz[pid] = contrib.z;
+                if (path_len) path_len[pid] = bounce + 1;
+            }
+        }
+        /* compaction: one atomic per warp, survivors packed in lane order */
+        __syncwarp();
+        uint32_t mask = __ballot_sync(0xffffffffu, alive);
+        if (mask) {
+            uint32_t base = 0;
+            int leader = __ffs(mask) - 1;
+            if ((int)lane == leader) base = atomicAdd(count_out, (uint32_t)__popc(mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (alive) {
+                uint32_t j = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+                qout.ox[j] = next.o.x; qout.oy[j] = next.o.y; qout.oz[j] = next.o.z;
+                qout.dx[j] = next.d.x; qout.dy[j] = next.d.y; qout.dz[j] = next.d.z;
+                qout.tm[j] = next.tm;
+                qout.bx[j] = beta.x; qout.by[j] = beta.y; qout.bz[j] = beta.z;
+                qout.pid[j] = pid;
+                qout.rng[j] = pos;
+            }
+        }
+    }
+}
+
+/* pixel_color += ray_color(...) over the wave's samples, in sample order (main.rs:144-151) */
+__global__ void k_accumulate(const double *cx, const double *cy, const double *cz, float *accum, uint32_t npix, uint32_t nsamples,
+                             int add) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    double sx = 0., sy = 0., sz = 0.;
+    for (uint32_t s = 0; s < nsamples; ++s) {
+        size_t k = (size_t)s * npix + p;
+        sx += cx[k];
+        sy += cy[k];
+        sz += cz[k];
+    }
+    float *a = accum + 3 * (size_t)p;
+    if (add) {
+        a[0] += (float)sx; a[1] += (float)sy; a[2] += (float)sz;
+    } else {
+        a[0] = (float)sx; a[1] = (float)sy; a[2] = (float)sz;
+    }
+}
+
+/* dumped-ray batch: BvhNode::hit + the record of the winner */
+__global__ void __launch_bounds__(kThreads) k_trace_batch(DScene sc, const rtgpu_ray *rays, const uint64_t *keys, rtgpu_hit *out, int64_t n) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        rtgpu_ray q = rays[i];
+        Ray r;
+        r.o = v3(q.o[0], q.o[1], q.o[2]);
+        r.d = v3(q.d[0], q.d[1], q.d[2]);
+        r.tm = q.tm;
+        rt_rng rng;
+        rng.init(keys ? keys[i] : (uint64_t)i, 0, 0, RT_DOMAIN_BATCH, 0);
+        Closest c = closest_hit<true>(sc, 0, sc.n_ops, r.o, r.d, r.tm, q.t_min, q.t_max, &rng);
+        rtgpu_hit h;
+        memset(&h, 0, sizeof h);
+        h.gid = -1;
+        h.inst = -1;
+        h.mat = -1;
+        h.rng_pos = rng.pos;
+        if (c.op != RT_NO_HIT) {
+            HitRec rec;
+            make_record(sc, r, c.t, c.op, c.face, rec);
+            h.hit = 1;
+            h.t = rec.t;
+            h.p[0] = rec.p.x; h.p[1] = rec.p.y; h.p[2] = rec.p.z;
+            h.n[0] = rec.n.x; h.n[1] = rec.n.y; h.n[2] = rec.n.z;
+            h.u = rec.u;
+            h.v = rec.v;
+            h.front_face = rec.front ? 1 : 0;
+            h.gid = rec.gid;
+            h.face = rec.face;
+            h.inst = rec.inst;
+            h.mat = (int32_t)rec.mat;
+        }
+        out[i] = h;
+    }
+}
+
+__global__ void k_camera_rays(DScene sc, WaveParams wp, rtgpu_ray *out, uint32_t *rng_pos) {
+    uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid >= wp.n_paths) return;
+    uint32_t pixel = wp.first_pixel + pid % wp.npix_wave;
+    rt_rng rng;
+    path_rng(rng, wp, pid, 0);
+    Ray r = camera_ray(sc.cam, (int)(pixel % (uint32_t)wp.width), (int)(pixel / (uint32_t)wp.width), wp.width, wp.height, rng);
+    rtgpu_ray q;
+    q.o[0] = r.o.x; q.o[1] = r.o.y; q.o[2] = r.o.z;
+    q.d[0] = r.d.x; q.d[1] = r.d.y; q.d[2] = r.d.z;
+    q.tm = r.tm;
+    q.t_min = 0.001;
+    q.t_max = RT_F64_MAX;
+    out[pid] = q;
+    if (rng_pos) rng_pos[pid] = rng.pos;
+}
+
+/* write_color (main.rs:280-299) + the row flip of main.rs:197 */
+__global__ void k_resolve(const float *accum, int w, int h, int spp, uint8_t *rgb8) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= w * h) return;
+    int x = p % w, y = p / w;
+    uint8_t *o = rgb8 + 3 * ((size_t)(h - y - 1) * w + x);
+    for (int c = 0; c < 3; ++c) {
+        double r = (double)accum[3 * (size_t)p + c];
+        if (r != r) r = 0.;
+        double v = sqrt(r / (double)spp);
+        if (v < 0.0) v = 0.0;
+        if (v > 0.999) v = 0.999; /* f64::clamp keeps NaN; `as u8` maps it to 0 */
+        double f = floor(v * 255.999);
+        o[c] = (f != f) ? 0 : (f <= 0. ? 0 : (f >= 255. ? 255 : (uint8_t)f));
+    }
+}
+
+} // namespace
+
+/* --------------------------------------------------------------------------------------------- */
+struct rtgpu_scene {
+    int device = 0;
+    DScene d;
+    std::vector<void *> allocs;
+    /* wave buffers, grown on demand */
+    size_t cap = 0;
+    void *wave_mem = nullptr;
+    PathQueue q[2];
+    HitBuf hb;
+    double *cx = nullptr, *cy = nullptr, *cz = nullptr;
+    uint32_t *path_len = nullptr;
+    uint32_t *counts = nullptr;      /* device, RTGPU_MAX_BOUNCE_STATS*4 + ... */
+    uint32_t *counts_host = nullptr; /* pinned */
+    int max_counts = 0;
+    float *accum_dev = nullptr;
+    size_t accum_cap = 0;
+    std::vector<cudaEvent_t> events;
+};
+
+namespace {
+
+template <typename T>
+rtgpu_status upload(rtgpu_scene *s, const T *src, size_t n, const T **dst) {
+    void *p = nullptr;
+    size_t bytes = (n ? n : 1) * sizeof(T);
+    CK(cudaMalloc(&p, bytes));
+    s->allocs.push_back(p);
+    if (n) CK(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = reinterpret_cast<const T *>(p);
+    return RTGPU_OK;
+}
+
+rtgpu_status validate(const rtgpu_scene_desc *d) {
+    auto bad = [](const char *m) {
+        g_err = m;
+        return RTGPU_ERR_INVALID_SCENE;
+    };
+    if (!d || !d->ops || d->n_ops == 0) return bad("empty traversal program (the reference panics on an empty BvhNode)");
+    if (d->n_ops >= 0x1fffffffu) return bad("traversal program too long");
+    if (d->max_push_depth > RT_MAX_PUSH) return bad("wrapper nesting deeper than RT_MAX_PUSH");
+    if (d->n_ctxs == 0) return bad("no contexts");
+    for (uint32_t i = 0; i < d->n_ctxs; ++i) {
+        if (d->ctxs[i].len > RT_MAX_CHAIN) return bad("more than RT_MAX_CHAIN wrappers around one primitive");
+        if ((uint64_t)d->ctxs[i].start + d->ctxs[i].len > d->n_chain) return bad("context outside the chain array");
+    }
+    for (uint32_t i = 0; i < d->n_chain; ++i)
+        if (d->chain[i] >= d->n_xforms) return bad("chain entry outside the xform array");
+    int push = 0;
+    for (uint32_t i = 0; i < d->n_ops;) {
+        const rtgpu_op &op = d->ops[i];
+        uint32_t kind = op.kind_ctx & 0xff, ctx = op.kind_ctx >> 8;
+        uint32_t width = (kind == RTGPU_OP_MSPHERE || kind == RTGPU_OP_TRI) ? 2 : 1;
+        if (i + width > d->n_ops) return bad("two-slot op at the end of the program");
+        switch (kind) {
+        case RTGPU_OP_NODE:
+        case RTGPU_OP_MEDIUM:
+            if (op.skip <= i || op.skip > d->n_ops) return bad("skip index out of range");
+            break;
+        case RTGPU_OP_PUSH:
+            if ((uint64_t)op.a + op.b > d->n_chain) return bad("PUSH chain out of range");
+            ++push;
+            break;
+        case RTGPU_OP_POP:
+            if (--push < 0) return bad("POP without PUSH");
+            break;
+        default:
+            if (kind > RTGPU_OP_POP) return bad("unknown op kind");
+            break;
+        }
+        if (kind != RTGPU_OP_NODE && kind != RTGPU_OP_PUSH && kind != RTGPU_OP_POP) {
+            if (ctx >= d->n_ctxs) return bad("context id out of range");
+            if (op.a >= d->n_materials) return bad("material id out of range");
+        }
+        i += width;
+    }
+    if (push != 0) return bad("unbalanced PUSH/POP");
+    for (uint32_t i = 0; i < d->n_materials; ++i) {
+        const rtgpu_material &m = d->materials[i];
+        if (m.kind > 4) return bad("unknown material kind");
+        if ((m.kind == 0 || m.kind == 3 || m.kind == 4) && m.tex >= d->n_textures) return bad("texture id out of range");
+    }
+    for (uint32_t i = 0; i < d->n_textures; ++i) {
+        const rtgpu_texture &t = d->textures[i];
+        if (t.kind > 3) return bad("unknown texture kind");
+        if (t.kind == 1 && (t.a < 0 || t.b < 0 || (uint32_t)t.a >= i || (uint32_t)t.b >= i)) return bad("checker sub-texture must precede it");
+        if (t.kind == 2 && (t.a < 0 || (uint32_t)t.a >= d->n_perlins)) return bad("perlin id out of range");
+        if (t.kind == 3 && t.a >= (int32_t)d->n_images) return bad("image id out of range");
+    }
+    for (uint32_t i = 0; i < d->n_images; ++i) {
+        const rtgpu_image &im = d->images[i];
+        if (im.width <= 0 || im.height <= 0 || im.offset < 0 ||
+            (uint64_t)im.offset + (uint64_t)im.width * (uint64_t)im.height * 3 > d->n_texel_bytes)
+            return bad("image outside the texel buffer");
+    }
+    for (uint32_t i = 0; i < d->n_lights; ++i)
+        if (d->lights[i].kind > RTGPU_LIGHT_DEAD) return bad("unknown light kind");
+    return RTGPU_OK;
+}
+
+int grid_blocks() { return kSMs * kBlocksPerSM; }
+
+rtgpu_status ensure_wave(rtgpu_scene *s, size_t n_paths, int max_depth) {
+    if (max_depth + 2 > s->max_counts) {
+        if (s->counts) cudaFree(s->counts);
+        if (s->counts_host) cudaFreeHost(s->counts_host);
+        s->counts = nullptr;
+        s->counts_host = nullptr;
+        s->max_counts = max_depth + 2;
+        CK(cudaMalloc(&s->counts, sizeof(uint32_t) * (size_t)s->max_counts));
+        CK(cudaMallocHost(&s->counts_host, sizeof(uint32_t) * (size_t)s->max_counts));
+    }
+    if (n_paths <= s->cap) return RTGPU_OK;
+    if (s->wave_mem) cudaFree(s->wave_mem);
+    s->wave_mem = nullptr;
+    s->cap = 0;
+    size_t n = (n_paths + 255) & ~(size_t)255;
+    /* per path: 2 queues x (10 doubles + 2 u32) + hit (double + u32) + contrib (3 doubles) + path_len */
+    size_t bytes = n * (2 * (10 * 8 + 2 * 4) + 8 + 4 + 3 * 8 + 4);
+    CK(cudaMalloc(&s->wave_mem, bytes));
+    char *p = static_cast<char *>(s->wave_mem);
+    auto take_d = [&](double *&dst) { dst = reinterpret_cast<double *>(p); p += n * 8; };
+    auto take_u = [&](uint32_t *&dst) { dst = reinterpret_cast<uint32_t *>(p); p += n * 4; };
+    for (int k = 0; k < 2; ++k) {
+        PathQueue &q = s->q[k];
+        take_d(q.ox); take_d(q.oy); take_d(q.oz); take_d(q.dx); take_d(q.dy); take_d(q.dz); take_d(q.tm);
+        take_d(q.bx); take_d(q.by); take_d(q.bz);
+    }
+    take_d(s->hb.t);
+    take_d(s->cx); take_d(s->cy); take_d(s->cz);
+    for (int k = 0; k < 2; ++k) { take_u(s->q[k].pid); take_u(s->q[k].rng); }
+    take_u(s->hb.op);
+    take_u(s->path_len);
+    s->cap = n;
+    return RTGPU_OK;
+}
+
+struct WaveTiming {
+    double ms_extend = 0, ms_shade = 0, ms_other = 0;
+    uint64_t launches = 0, launches_extend = 0;
+};
+
+/* Enqueues one whole wave on `stream`; contributions end in s->cx/cy/cz[0 .. n_paths). */
+rtgpu_status run_wave(rtgpu_scene *s, const WaveParams &wp, int max_depth, cudaStream_t stream, bool want_len, bool timing,
+                      WaveTiming *wt, uint64_t *rays, uint64_t *rays_per_bounce) {
+    rtgpu_status st = ensure_wave(s, wp.n_paths, max_depth);
+    if (st != RTGPU_OK) return st;
+    size_t n = wp.n_paths;
+    CK(cudaMemsetAsync(s->counts, 0, sizeof(uint32_t) * (size_t)s->max_counts, stream));
+    CK(cudaMemcpyAsync(s->counts, &wp.n_paths, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemsetAsync(s->cx, 0, n * 8, stream));
+    CK(cudaMemsetAsync(s->cy, 0, n * 8, stream));
+    CK(cudaMemsetAsync(s->cz, 0, n * 8, stream));
+    if (want_len) CK(cudaMemsetAsync(s->path_len, 0, n * 4, stream));
+    size_t n_ev = timing ? (size_t)(2 * max_depth + 2) : 0;
+    while (s->events.size() < n_ev) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        s->events.push_back(e);
+    }
+    int blocks = grid_blocks();
+    size_t ev = 0;
+    if (timing) CK(cudaEventRecord(s->events[ev++], stream));
+    k_raygen<<<blocks, kThreads, 0, stream>>>(s->d, s->q[0], wp);
+    if (timing) CK(cudaEventRecord(s->events[ev++], stream));
+    for (int b = 0; b < max_depth; ++b) {
+        PathQueue &qin = s->q[b & 1], &qout = s->q[(b + 1) & 1];
+        k_extend<<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->counts + b, wp);
+        if (timing) CK(cudaEventRecord(s->events[ev++], stream));
+        k_shade<<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, qout, s->counts + b, s->counts + b + 1, s->cx, s->cy, s->cz,
+                                                 want_len ? s->path_len : nullptr, wp, (uint32_t)b);
+        if (timing) CK(cudaEventRecord(s->events[ev++], stream));
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(s->counts_host, s->counts, sizeof(uint32_t) * (size_t)(max_depth + 1), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    for (int b = 0; b < max_depth; ++b) {
+        *rays += s->counts_host[b];
+        if (rays_per_bounce && b < RTGPU_MAX_BOUNCE_STATS) rays_per_bounce[b] += s->counts_host[b];
+    }
+    if (wt) {
+        wt->launches += 1 + 2 * (uint64_t)max_depth;
+        wt->launches_extend += (uint64_t)max_depth;
+        if (timing) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, s->events[0], s->events[1]));
+            wt->ms_other += ms;
+            for (int b = 0; b < max_depth; ++b) {
+                CK(cudaEventElapsedTime(&ms, s->events[1 + 2 * b], s->events[2 + 2 * b]));
+                wt->ms_extend += ms;
+                CK(cudaEventElapsedTime(&ms, s->events[2 + 2 * b], s->events[3 + 2 * b]));
+                wt->ms_shade += ms;
+            }
+        }
+    }
+    return RTGPU_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *rtgpu_last_error(void) { return g_err.c_str(); }
+
+int rtgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_scene **out) {
+    if (!out) {
+        g_err = "out is NULL";
+        return RTGPU_ERR_INVALID_ARG;
+    }
+    *out = nullptr;
+    rtgpu_status st = validate(desc);
+    if (st != RTGPU_OK) return st;
+    if (device >= 0) CK(cudaSetDevice(device));
+    int cur = 0;
+    CK(cudaGetDevice(&cur));
+    rtgpu_scene *s = new (std::nothrow) rtgpu_scene();
+    if (!s) return RTGPU_ERR_OOM;
+    s->device = cur;
+    memset(&s->d, 0, sizeof s->d);
+#define UP(field, src, n)                                                                                          \
+    st = upload(s, src, (size_t)(n), &s->d.field);                                                                 \
+    if (st != RTGPU_OK) {                                                                                          \
+        rtgpu_scene_destroy(s);                                                                                    \
+        return st;                                                                                                 \
+    }
+    UP(ops, desc->ops, desc->n_ops)
+    UP(xforms, desc->xforms, desc->n_xforms)
+    UP(chain, desc->chain, desc->n_chain)
+    UP(ctxs, desc->ctxs, desc->n_ctxs)
+    UP(mats, desc->materials, desc->n_materials)
+    UP(texs, desc->textures, desc->n_textures)
+    UP(perlins, desc->perlins, desc->n_perlins)
+    UP(images, desc->images, desc->n_images)
+    UP(texels, desc->texels, desc->n_texel_bytes)
+    UP(lights, desc->lights, desc->n_lights)
+#undef UP
+    s->d.n_ops = desc->n_ops;
+    s->d.n_lights = desc->n_lights;
+    s->d.cam = desc->camera;
+    for (int c = 0; c < 3; ++c) s->d.background[c] = desc->background[c];
+    *out = s;
+    return RTGPU_OK;
+}
+
+rtgpu_status rtgpu_scene_destroy(rtgpu_scene *s) {
+    if (!s) return RTGPU_OK;
+    cudaSetDevice(s->device);
+    for (void *p : s->allocs) cudaFree(p);
+    if (s->wave_mem) cudaFree(s->wave_mem);
+    if (s->counts) cudaFree(s->counts);
+    if (s->counts_host) cudaFreeHost(s->counts_host);
+    if (s->accum_dev) cudaFree(s->accum_dev);
+    for (cudaEvent_t e : s->events) cudaEventDestroy(e);
+    delete s;
+    return RTGPU_OK;
+}
+
+rtgpu_status rtgpu_render(rtgpu_scene *s, const rtgpu_render_params *p, float *accum, rtgpu_stats *stats) {
+    if (!s || !p || !accum) {
+        g_err = "NULL argument";
+        return RTGPU_ERR_INVALID_ARG;
+    }
+    if (p->width < 2 || p->height < 2 || p->spp_end < p->spp_begin || p->max_depth < 0 || p->max_depth > 4096) {
+        g_err = "bad render parameters (width/height >= 2: u = (x+xi)/(W-1), main.rs:147)";
+        return RTGPU_ERR_INVALID_ARG;
+    }
+    if (!(s->d.cam.time0 < s->d.cam.time1)) {
+        g_err = "camera shutter is empty: gen_range(time0..time1) panics upstream (camera.rs:71)";
+        return RTGPU_ERR_INVALID_SCENE;
+    }
+    CK(cudaSetDevice(s->device));
+    cudaStream_t stream = static_cast<cudaStream_t>(p->stream);
+    size_t npix = (size_t)p->width * (size_t)p->height;
+    if (npix > 0x7fffffffu) {
+        g_err = "image too large";
+        return RTGPU_ERR_INVALID_ARG;
+    }
+    size_t max_paths = p->max_paths_in_flight > 0 ? (size_t)p->max_paths_in_flight : ((size_t)1 << 24);
+    if (max_paths < npix) max_paths = npix;
+    if (max_paths > 0xfffffff0u) max_paths = 0xfffffff0u;
+    int spp_per_wave = (int)(max_paths / npix);
+    if (spp_per_wave < 1) spp_per_wave = 1;
+
+    float *acc_dev = accum;
+    if (!p->accum_on_device) {
+        if (s->accum_cap < npix * 3) {
+            if (s->accum_dev) cudaFree(s->accum_dev);
+            s->accum_dev = nullptr;
+            s->accum_cap = 0;
+            CK(cudaMalloc(&s->accum_dev, npix * 3 * sizeof(float)));
+            s->accum_cap = npix * 3;
+        }
+        acc_dev = s->accum_dev;
+        if (p->accumulate) CK(cudaMemcpyAsync(acc_dev, accum, npix * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
+    }
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, stream));
+    WaveTiming wt;
+    uint64_t rays = 0;
+    uint64_t per_bounce[RTGPU_MAX_BOUNCE_STATS];
+    memset(per_bounce, 0, sizeof per_bounce);
+    bool first = true;
+    if (p->spp_end == p->spp_begin && !p->accumulate) CK(cudaMemsetAsync(acc_dev, 0, npix * 3 * sizeof(float), stream));
+    for (int sb = p->spp_begin; sb < p->spp_end; sb += spp_per_wave) {
+        int ns = p->spp_end - sb < spp_per_wave ? p->spp_end - sb : spp_per_wave;
+        WaveParams wp;
+        wp.seed = p->seed;
+        wp.first_pixel = 0;
+        wp.npix_wave = (uint32_t)npix;
+        wp.sample_begin = (uint32_t)sb;
+        wp.n_paths = (uint32_t)(npix * (size_t)ns);
+        wp.width = p->width;
+        wp.height = p->height;
+        rtgpu_status st = run_wave(s, wp, p->max_depth, stream, false, stats != nullptr, &wt, &rays, per_bounce);
+        if (st != RTGPU_OK) return st;
+        k_accumulate<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(s->cx, s->cy, s->cz, acc_dev, (uint32_t)npix, (uint32_t)ns,
+                                                                          (first && !p->accumulate) ? 0 : 1);
+        wt.launches += 1;
+        first = false;
+    }
+    CK(cudaGetLastError());
+    if (!p->accum_on_device) CK(cudaMemcpyAsync(accum, acc_dev, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CK(cudaEventRecord(e1, stream));
+    CK(cudaStreamSynchronize(stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->rays = rays;
+        stats->samples = (uint64_t)npix * (uint64_t)(p->spp_end - p->spp_begin);
+        stats->ms_total = ms;
+        stats->ms_extend = wt.ms_extend;
+        stats->ms_shade = wt.ms_shade;
+        stats->ms_other = wt.ms_other;
+        stats->launches = wt.launches;
+        stats->launches_extend = wt.launches_extend;
+        memcpy(stats->rays_per_bounce, per_bounce, sizeof per_bounce);
+    }
+    return RTGPU_OK;
+}
+
+rtgpu_status rtgpu_trace_batch(rtgpu_scene *s, const rtgpu_ray *rays, int64_t n, const uint64_t *keys, rtgpu_hit *out,
+                               double *ms_kernel) {
+    if (!s || (n > 0 && (!rays || !out)) || n < 0) {
+        g_err = "bad argument";
+        return RTGPU_ERR_INVALID_ARG;
+    }
+    if (ms_kernel) *ms_kernel = 0.;
+    if (n == 0) return RTGPU_OK;
+    CK(cudaSetDevice(s->device));
+    rtgpu_ray *d_rays = nullptr;
+    uint64_t *d_keys = nullptr;
+    rtgpu_hit *d_out = nullptr;
+    rtgpu_status st = RTGPU_OK;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto body = [&]() -> rtgpu_status {
+        CK(cudaMalloc(&d_rays, (size_t)n * sizeof(rtgpu_ray)));
+        CK(cudaMalloc(&d_out, (size_t)n * sizeof(rtgpu_hit)));
+        CK(cudaMemcpy(d_rays, rays, (size_t)n * sizeof(rtgpu_ray), cudaMemcpyHostToDevice));
+        if (keys) {
+            CK(cudaMalloc(&d_keys, (size_t)n * sizeof(uint64_t)));
+            CK(cudaMemcpy(d_keys, keys, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        }
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0, 0));
+        k_trace_batch<<<grid_blocks(), kThreads>>>(s->d, d_rays, d_keys, d_out, n);
+        CK(cudaEventRecord(e1, 0));
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms_kernel) *ms_kernel = ms;
+        CK(cudaMemcpy(out, d_out, (size_t)n * sizeof(rtgpu_hit), cudaMemcpyDeviceToHost));
+        return RTGPU_OK;
+    };
+    st = body();
+    if (d_rays) cudaFree(d_rays);
+    if (d_keys) cudaFree(d_keys);
+    if (d_out) cudaFree(d_out);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    return st;
+}
+
+rtgpu_status rtgpu_camera_rays(rtgpu_scene *s, int32_t width, int32_t height, int64_t first_pixel, int64_t n, int32_t k,
+                               uint64_t seed, rtgpu_ray *out, uint32_t *rng_pos) {
+    if (!s || !out || n <= 0 || width < 2 || height < 2 || first_pixel < 0 || first_pixel + n > (int64_t)width * height) {
+        g_err = "bad argument";
+        return RTGPU_ERR_INVALID_ARG;
+    }
+    CK(cudaSetDevice(s->device));
+    rtgpu_ray *d_out = nullptr;
+    uint32_t *d_pos = nullptr;
+    auto body = [&]() -> rtgpu_status {
+        CK(cudaMalloc(&d_out, (size_t)n * sizeof(rtgpu_ray)));
+        CK(cudaMalloc(&d_pos, (size_t)n * sizeof(uint32_t)));
+        WaveParams wp;
+        wp.seed = seed;
+        wp.first_pixel = (uint32_t)first_pixel;
+        wp.npix_wave = (uint32_t)n;
+        wp.sample_begin = (uint32_t)k;
+        wp.n_paths = (uint32_t)n;
+        wp.width = width;
+        wp.height = height;
+        k_camera_rays<<<(unsigned)((n + 127) / 128), 128>>>(s->d, wp, d_out, d_pos);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(out, d_out, (size_t)n * sizeof(rtgpu_ray), cudaMemcpyDeviceToHost));
+        if (rng_pos) CK(cudaMemcpy(rng_pos, d_pos, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        return RTGPU_OK;
+    };
+    rtgpu_status st = body();
+    if (d_out) cudaFree(d_out);
+    if (d_pos) cudaFree(d_pos);
+    return st;
+}
+
+rtgpu_status rtgpu_sample_radiance(rtgpu_scene *s, int32_t width, int32_t height, int64_t first_pixel, int64_t n, int32_t k,
+                                   int32_t max_depth, uint64_t seed, double *out_rgb, uint32_t *out_rays) {
+    if (!s || !out_rgb || n <= 0 || width < 2 || height < 2 || first_pixel < 0 || first_pixel + n > (int64_t)width * height ||
+        max_depth < 0 || max_depth > 4096) {
+        g_err = "bad argument";
+        return RTGPU_ERR_INVALID_ARG;
+    }
+    CK(cudaSetDevice(s->device));
+    WaveParams wp;
+    wp.seed = seed;
+    wp.first_pixel = (uint32_t)first_pixel;
+    wp.npix_wave = (uint32_t)n;
+    wp.sample_begin = (uint32_t)k;
+    wp.n_paths = (uint32_t)n;
+    wp.width = width;
+    wp.height = height;
+    uint64_t rays = 0;
+    rtgpu_status st = run_wave(s, wp, max_depth, 0, true, false, nullptr, &rays, nullptr);
+    if (st != RTGPU_OK) return st;
+    std::vector<double> tmp((size_t)n * 3);
+    CK(cudaMemcpy(tmp.data(), s->cx, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(tmp.data() + n, s->cy, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(tmp.data() + 2 * n, s->cz, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n; ++i) {
+        out_rgb[3 * i] = tmp[(size_t)i];
+        out_rgb[3 * i + 1] = tmp[(size_t)(n + i)];
+        out_rgb[3 * i + 2] = tmp[(size_t)(2 * n + i)];
+    }
+    if (out_rays) {
+        CK(cudaMemcpy(out_rays, s->path_len, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < n; ++i)
+            if (out_rays[i] == 0) out_rays[i] = (uint32_t)max_depth; /* still alive after max_depth segments */
+    }
+    return RTGPU_OK;
+}
+
+rtgpu_status rtgpu_resolve(const float *accum, int32_t width, int32_t height, int32_t spp, int32_t accum_on_device, uint8_t *rgb8) {
+    if (!accum || !rgb8 || width <= 0 || height <= 0 || spp <= 0) {
+        g_err = "bad argument";
+        return RTGPU_ERR_INVALID_ARG;
+    }
+    size_t npix = (size_t)width * (size_t)height;
+    float *d_acc = nullptr;
+    uint8_t *d_rgb = nullptr;
+    auto body = [&]() -> rtgpu_status {
+        const float *src = accum;
+        if (!accum_on_device) {
+            CK(cudaMalloc(&d_acc, npix * 3 * sizeof(float)));
+            CK(cudaMemcpy(d_acc, accum, npix * 3 * sizeof(float), cudaMemcpyHostToDevice));
+            src = d_acc;
+        }
+        CK(cudaMalloc(&d_rgb, npix * 3));
+        k_resolve<<<(unsigned)((npix + 255) / 256), 256>>>(src, width, height, spp, d_rgb);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(rgb8, d_rgb, npix * 3, cudaMemcpyDeviceToHost));
+        return RTGPU_OK;
+    };
+    rtgpu_status st = body();
+    if (d_acc) cudaFree(d_acc);
+    if (d_rgb) cudaFree(d_rgb);
+    return st;
+}
+
+} // extern "C"
