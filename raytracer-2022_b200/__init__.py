@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
 ASSET_DIR = os.path.join(REPO_ROOT, "assets")
 HOST_LIB_PATH = os.path.join(_HERE, "librthost.so")
-GPU_LIB_PATH = os.path.join(_HERE, "librtgpu.so")
+GPU_LIB_PATH = os.environ.get("RTGPU_LIB_PATH") or os.path.join(_HERE, "librtgpu.so")  # override: A/B builds only
 
 _host = None
 _gpu = None

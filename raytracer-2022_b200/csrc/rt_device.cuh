@@ -100,7 +100,14 @@ __device__ __forceinline__ void xform_ray(const rtgpu_xform &xf, V3 &o, V3 &d) {
         break;
     }
 }
-__device__ __forceinline__ rtgpu_xform load_xform(const DScene &sc, uint32_t chain_idx) {
+/* the three arrays traversal needs, passed by value (kept in registers / the param bank) */
+struct TravScene {
+    const rtgpu_op *ops;
+    const rtgpu_xform *xforms;
+    const uint32_t *chain;
+};
+__device__ __forceinline__ TravScene trav_of(const DScene &sc) { return TravScene{sc.ops, sc.xforms, sc.chain}; }
+__device__ __forceinline__ rtgpu_xform load_xform(const TravScene &sc, uint32_t chain_idx) {
     const rtgpu_xform *x = sc.xforms + __ldg(sc.chain + chain_idx);
     const double2 *p = reinterpret_cast<const double2 *>(x);
     rtgpu_xform r;
@@ -169,21 +176,24 @@ __device__ __forceinline__ bool hit_triangle(V3 o, V3 d, V3 a, V3 b, V3 c, V3 n,
     best = t;
     return true;
 }
-/* AABB::hit, aabb.rs:15-32.  inv = 1/dir is what upstream recomputes per node; one final
- * `t_max <= t_min` test is equivalent to the per-axis early exits (bounds are monotone). */
-__device__ __forceinline__ bool hit_aabb(V3 o, V3 inv, const double b[6], double tmin, double tmax) {
-    double t0 = (b[0] - o.x) * inv.x, t1 = (b[3] - o.x) * inv.x;
-    if (inv.x < 0.) { double s = t0; t0 = t1; t1 = s; }
+/* AABB::hit, aabb.rs:15-32.  inv = 1/dir is what upstream recomputes per node.  Upstream
+ * computes t0 from min, t1 from max and swaps them when inv < 0; picking the near/far plane by
+ * the sign first yields the same two values without the swap.  One final `t_max <= t_min` test
+ * is equivalent to the per-axis early exits (both bounds are monotone).  The comparisons keep
+ * upstream's polarity, so NaN (0 * inf) leaves a bound unchanged. */
+struct RaySigns {
+    bool x, y, z; /* inv.* < 0 */
+};
+__device__ __forceinline__ bool hit_aabb(V3 o, V3 inv, RaySigns sg, const double b[6], double tmin, double tmax) {
+    double t0 = ((sg.x ? b[3] : b[0]) - o.x) * inv.x, t1 = ((sg.x ? b[0] : b[3]) - o.x) * inv.x;
     tmin = t0 > tmin ? t0 : tmin;
     tmax = t1 < tmax ? t1 : tmax;
-    if (tmax <= tmin) return false;
-    t0 = (b[1] - o.y) * inv.y; t1 = (b[4] - o.y) * inv.y;
-    if (inv.y < 0.) { double s = t0; t0 = t1; t1 = s; }
+    t0 = ((sg.y ? b[4] : b[1]) - o.y) * inv.y;
+    t1 = ((sg.y ? b[1] : b[4]) - o.y) * inv.y;
     tmin = t0 > tmin ? t0 : tmin;
     tmax = t1 < tmax ? t1 : tmax;
-    if (tmax <= tmin) return false;
-    t0 = (b[2] - o.z) * inv.z; t1 = (b[5] - o.z) * inv.z;
-    if (inv.z < 0.) { double s = t0; t0 = t1; t1 = s; }
+    t0 = ((sg.z ? b[5] : b[2]) - o.z) * inv.z;
+    t1 = ((sg.z ? b[2] : b[5]) - o.z) * inv.z;
     tmin = t0 > tmin ? t0 : tmin;
     tmax = t1 < tmax ? t1 : tmax;
     return !(tmax <= tmin);
@@ -197,87 +207,143 @@ struct Closest {
 };
 
 /* Walks ops [begin, end) in order -- the reference's left-then-right recursion unrolled
- * (SURVEY.md 2.5).  MAIN = false is the boundary walk of a ConstantMedium (no nested media,
- * no rng).  `rng` draws the medium's free path (constantmedium.rs:60) in visiting order. */
-template <bool MAIN>
-__device__ __noinline__ Closest closest_hit(const DScene &sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm,
-                                            double tmin, double tmax, rt_rng *rng) {
+ * (SURVEY.md 2.5).  The loop is "while-while": a tight run over consecutive NODE ops, then one
+ * leaf op, so that the lanes of a warp spend most iterations in the same code.
+ * MAIN = false is the boundary walk of a ConstantMedium (no nested media, no rng).
+ * `rng` draws the medium's free path (constantmedium.rs:60) in visiting order. */
+struct RayState {
+    V3 o, d, inv;
+    double a; /* |d|^2 */
+    RaySigns sg;
+};
+__device__ __forceinline__ void ray_state_derive(RayState &r) {
+    r.inv = v3(1. / r.d.x, 1. / r.d.y, 1. / r.d.z);
+    r.a = length_sqr(r.d);
+    r.sg.x = r.inv.x < 0.;
+    r.sg.y = r.inv.y < 0.;
+    r.sg.z = r.inv.z < 0.;
+}
+
+struct Traversal;
+__device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm,
+                                                     double tmin, double tmax);
+
+/* Resumable walk: start(), then step() until done().  One step = a run of NODE ops + one leaf. */
+struct Traversal {
+    RayState r;
+    double tm, tmin;
     Closest best;
-    best.t = tmax;
-    best.op = RT_NO_HIT;
-    best.face = 0;
-    V3 inv = v3(1. / d.x, 1. / d.y, 1. / d.z);
-    double a = length_sqr(d);
+    uint32_t i, end;
+    int sp;
     V3 saved_o[RT_MAX_PUSH], saved_d[RT_MAX_PUSH];
-    int sp = 0;
-    uint32_t i = begin;
-    while (i < end) {
+
+    __device__ __forceinline__ void start(uint32_t begin, uint32_t end_, V3 o, V3 d, double tm_, double tmin_, double tmax) {
+        best.t = tmax;
+        best.op = RT_NO_HIT;
+        best.face = 0;
+        r.o = o;
+        r.d = d;
+        ray_state_derive(r);
+        tm = tm_;
+        tmin = tmin_;
+        i = begin;
+        end = end_;
+        sp = 0;
+    }
+    __device__ __forceinline__ bool done() const { return i >= end; }
+
+    /* DRAW() returns the next uniform of the ray's stream (ConstantMedium free path) */
+    template <bool MAIN, typename DRAW>
+    __device__ __forceinline__ void step(const TravScene sc, DRAW &&draw) {
         const rtgpu_op *op = sc.ops + i;
         uint4 h = load_op_header(op);
         uint32_t kind = h.x & 0xffu;
         double p[6];
+        /* ---- run of BvhNode boxes ---- */
+        while (kind == RTGPU_OP_NODE) {
+            load_op_payload(op, p);
+            i = hit_aabb(r.o, r.inv, r.sg, p, tmin, best.t) ? i + 1 : h.y;
+            if (i >= end) return;
+            op = sc.ops + i;
+            h = load_op_header(op);
+            kind = h.x & 0xffu;
+        }
+        /* ---- one leaf / control op ---- */
         if (kind != RTGPU_OP_POP) load_op_payload(op, p);
         switch (kind) {
-        case RTGPU_OP_NODE:
-            i = hit_aabb(o, inv, p, tmin, best.t) ? i + 1 : h.y;
-            break;
         case RTGPU_OP_SPHERE:
-            if (hit_sphere(o, d, a, v3(p[0], p[1], p[2]), p[3], tmin, best.t)) best.op = i;
+            if (hit_sphere(r.o, r.d, r.a, v3(p[0], p[1], p[2]), p[3], tmin, best.t)) best.op = i;
             i += 1;
             break;
+        case RTGPU_OP_BOX:
+            if (hit_box(r.o, r.d, p, tmin, best.t, best.face)) best.op = i;
+            i += 1;
+            break;
+        case RTGPU_OP_TRI: {
+            double q[8];
+            load_slot8(op + 1, q);
+            if (hit_triangle(r.o, r.d, v3(p[0], p[1], p[2]), v3(p[3], p[4], p[5]), v3(q[0], q[1], q[2]), v3(q[3], q[4], q[5]),
+                             tmin, best.t))
+                best.op = i;
+            i += 2;
+            break;
+        }
         case RTGPU_OP_MSPHERE: {
             double q[8];
             load_slot8(op + 1, q);
             /* MovingSphere::center, sphere.rs:124-127 */
             V3 c0 = v3(p[0], p[1], p[2]), c1 = v3(q[0], q[1], q[2]);
             V3 c = c0 + (c1 - c0) * ((tm - p[4]) / (p[5] - p[4]));
-            if (hit_sphere(o, d, a, c, p[3], tmin, best.t)) best.op = i;
+            if (hit_sphere(r.o, r.d, r.a, c, p[3], tmin, best.t)) best.op = i;
             i += 2;
             break;
         }
         case RTGPU_OP_RECT_XY:
-            if (hit_rect<2>(o, d, p[0], p[1], p[2], p[3], p[4], tmin, best.t)) best.op = i;
+            if (hit_rect<2>(r.o, r.d, p[0], p[1], p[2], p[3], p[4], tmin, best.t)) best.op = i;
             i += 1;
             break;
         case RTGPU_OP_RECT_XZ:
-            if (hit_rect<1>(o, d, p[0], p[1], p[2], p[3], p[4], tmin, best.t)) best.op = i;
+            if (hit_rect<1>(r.o, r.d, p[0], p[1], p[2], p[3], p[4], tmin, best.t)) best.op = i;
             i += 1;
             break;
         case RTGPU_OP_RECT_YZ:
-            if (hit_rect<0>(o, d, p[0], p[1], p[2], p[3], p[4], tmin, best.t)) best.op = i;
+            if (hit_rect<0>(r.o, r.d, p[0], p[1], p[2], p[3], p[4], tmin, best.t)) best.op = i;
             i += 1;
             break;
-        case RTGPU_OP_BOX:
-            if (hit_box(o, d, p, tmin, best.t, best.face)) best.op = i;
-            i += 1;
-            break;
-        case RTGPU_OP_TRI: {
-            double q[8];
-            load_slot8(op + 1, q);
-            if (hit_triangle(o, d, v3(p[0], p[1], p[2]), v3(p[3], p[4], p[5]), v3(q[0], q[1], q[2]), v3(q[3], q[4], q[5]),
-                             tmin, best.t))
-                best.op = i;
-            i += 2;
-            break;
-        }
         case RTGPU_OP_MEDIUM:
-            if (MAIN) { /* ConstantMedium::hit, constantmedium.rs:49-83 */
-                Closest r1 = closest_hit<false>(sc, i + 1, h.y, o, d, tm, -CUDART_INF, CUDART_INF, nullptr);
-                if (r1.op != RT_NO_HIT) {
-                    Closest r2 = closest_hit<false>(sc, i + 1, h.y, o, d, tm, r1.t + 0.0001, CUDART_INF, nullptr);
-                    if (r2.op != RT_NO_HIT) {
-                        double t1 = fmax(r1.t, tmin);
-                        double t2 = fmin(r2.t, best.t);
-                        if (!(t1 >= t2)) {
-                            t1 = fmax(t1, 0.);
-                            double ray_length = sqrt(a);
-                            double distance_inside_boundary = (t2 - t1) * ray_length;
-                            double rnd = rng->gen();
-                            double hit_distance = p[0] * log(rnd); /* neg_inv_density * rnd.log(E) */
-                            if (!(hit_distance > distance_inside_boundary)) {
-                                best.t = t1 + hit_distance / ray_length;
-                                best.op = i;
-                            }
+            if constexpr (MAIN) { /* ConstantMedium::hit, constantmedium.rs:49-83 */
+                double t1 = CUDART_INF, t2 = CUDART_INF;
+                bool h1, h2 = false;
+                bool single_sphere = h.y == i + 2;
+                if (single_sphere) single_sphere = (load_op_header(op + 1).x & 0xffu) == RTGPU_OP_SPHERE;
+                if (single_sphere) { /* boundary = one Sphere (both media of final_scene) */
+                    double bp[6];
+                    load_op_payload(op + 1, bp);
+                    V3 c = v3(bp[0], bp[1], bp[2]);
+                    h1 = hit_sphere(r.o, r.d, r.a, c, bp[3], -CUDART_INF, t1);
+                    if (h1) h2 = hit_sphere(r.o, r.d, r.a, c, bp[3], t1 + 0.0001, t2);
+                } else {
+                    Closest r1 = closest_hit_boundary(sc, i + 1, h.y, r.o, r.d, tm, -CUDART_INF, CUDART_INF);
+                    h1 = r1.op != RT_NO_HIT;
+                    t1 = r1.t;
+                    if (h1) {
+                        Closest r2 = closest_hit_boundary(sc, i + 1, h.y, r.o, r.d, tm, t1 + 0.0001, CUDART_INF);
+                        h2 = r2.op != RT_NO_HIT;
+                        t2 = r2.t;
+                    }
+                }
+                if (h1 && h2) {
+                    t1 = fmax(t1, tmin);
+                    t2 = fmin(t2, best.t);
+                    if (!(t1 >= t2)) {
+                        t1 = fmax(t1, 0.);
+                        double ray_length = sqrt(r.a);
+                        double distance_inside_boundary = (t2 - t1) * ray_length;
+                        double rnd = draw();
+                        double hit_distance = p[0] * log(rnd); /* neg_inv_density * rnd.log(E) */
+                        if (!(hit_distance > distance_inside_boundary)) {
+                            best.t = t1 + hit_distance / ray_length;
+                            best.op = i;
                         }
                     }
                 }
@@ -285,29 +351,46 @@ __device__ __noinline__ Closest closest_hit(const DScene &sc, uint32_t begin, ui
             i = h.y;
             break;
         case RTGPU_OP_PUSH: {
-            saved_o[sp] = o;
-            saved_d[sp] = d;
+            saved_o[sp] = r.o;
+            saved_d[sp] = r.d;
             ++sp;
             for (uint32_t j = 0; j < h.w; ++j) {
                 rtgpu_xform xf = load_xform(sc, h.z + j);
-                xform_ray(xf, o, d);
+                xform_ray(xf, r.o, r.d);
             }
-            inv = v3(1. / d.x, 1. / d.y, 1. / d.z);
-            a = length_sqr(d);
+            ray_state_derive(r);
             i += 1;
             break;
         }
         default: /* POP */
             --sp;
-            o = saved_o[sp];
-            d = saved_d[sp];
-            inv = v3(1. / d.x, 1. / d.y, 1. / d.z);
-            a = length_sqr(d);
+            r.o = saved_o[sp];
+            r.d = saved_d[sp];
+            ray_state_derive(r);
             i += 1;
             break;
         }
     }
-    return best;
+};
+
+/* boundary walk of a medium whose boundary is not a single sphere: rare, kept out of line */
+__device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm,
+                                                     double tmin, double tmax) {
+    Traversal tr;
+    tr.start(begin, end, o, d, tm, tmin, tmax);
+    while (!tr.done()) tr.step<false>(sc, []() { return 0.; });
+    return tr.best;
+}
+
+/* closest hit of one ray, run to completion (dumped batches, light probes) */
+template <typename DRAW>
+__device__ __forceinline__ Closest closest_hit(const DScene &sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm, double tmin,
+                                               double tmax, DRAW &&draw) {
+    Traversal tr;
+    tr.start(begin, end, o, d, tm, tmin, tmax);
+    TravScene ts = trav_of(sc);
+    while (!tr.done()) tr.step<true>(ts, draw);
+    return tr.best;
 }
 
 /* ---- HitRecord of the winner (hittable/mod.rs:18-57), rebuilt once per ray ------------------- */
@@ -353,7 +436,7 @@ __device__ __noinline__ void make_record(const DScene &sc, const Ray &wr, double
     V3 o = wr.o, d = wr.d;
     V3 dirs[RT_MAX_CHAIN];
     for (uint32_t j = 0; j < ctx.len; ++j) {
-        rtgpu_xform xf = load_xform(sc, ctx.start + j);
+        rtgpu_xform xf = load_xform(trav_of(sc), ctx.start + j);
         xform_ray(xf, o, d);
         dirs[j] = d;
     }
@@ -412,7 +495,7 @@ __device__ __noinline__ void make_record(const DScene &sc, const Ray &wr, double
     }
     /* innermost wrapper first: record back to world space (hittable/mod.rs:167-171,250-261,283-285,323-327) */
     for (int j = (int)ctx.len - 1; j >= 0; --j) {
-        rtgpu_xform xf = load_xform(sc, ctx.start + (uint32_t)j);
+        rtgpu_xform xf = load_xform(trav_of(sc), ctx.start + (uint32_t)j);
         if (rec.inst < 0) rec.inst = (int32_t)xf.gid;
         switch (xf.kind) {
         case RTGPU_XF_TRANSLATE:

@@ -99,19 +99,66 @@ __global__ void __launch_bounds__(kThreads) k_raygen(DScene sc, PathQueue q, Wav
     }
 }
 
-/* world.hit(r, 0.001, f64::MAX), main.rs:243 */
-__global__ void __launch_bounds__(kThreads) k_extend(DScene sc, PathQueue q, HitBuf hb, const uint32_t *count, WaveParams wp) {
-    uint32_t n = *count;
-    uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        V3 o = v3(q.ox[i], q.oy[i], q.oz[i]);
-        V3 d = v3(q.dx[i], q.dy[i], q.dz[i]);
-        rt_rng rng;
-        path_rng(rng, wp, q.pid[i], q.rng[i]);
-        Closest c = closest_hit<true>(sc, 0, sc.n_ops, o, d, q.tm[i], 0.001, RT_F64_MAX, &rng);
-        hb.t[i] = c.t;
-        hb.op[i] = c.op == RT_NO_HIT ? RT_NO_HIT : (c.op | (c.face << 29));
-        q.rng[i] = rng.pos;
+/* world.hit(r, 0.001, f64::MAX), main.rs:243 -- persistent warps with dynamic ray fetch.
+ * Rays of one warp need very different numbers of traversal steps; a lane whose ray is finished
+ * takes the next ray index from a global counter (one atomic per warp refill) instead of idling
+ * until the slowest lane is done. */
+#ifndef RT_EXTEND_MIN_BLOCKS
+#define RT_EXTEND_MIN_BLOCKS 4
+#endif
+#ifndef RT_EXTEND_REFILL
+#define RT_EXTEND_REFILL 8 /* refill when at least this many lanes are idle */
+#endif
+#ifndef RT_EXTEND_STEPS
+#define RT_EXTEND_STEPS 4 /* traversal steps between two refill checks */
+#endif
+__global__ void __launch_bounds__(kThreads, RT_EXTEND_MIN_BLOCKS) k_extend(DScene sc, PathQueue q, HitBuf hb, const uint32_t *count,
+                                                                           uint32_t *fetch, WaveParams wp) {
+    const uint32_t n = *count;
+    const uint32_t lane = threadIdx.x & 31u;
+    const TravScene ts = trav_of(sc);
+    Traversal tr;
+    bool active = false, exhausted = false;
+    uint32_t idx = 0, pid = 0, pos = 0;
+    for (;;) {
+        uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= RT_EXTEND_REFILL)) {
+            int leader = __ffs(idle) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(fetch, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            exhausted = base + (uint32_t)__popc(idle) >= n;
+            if (!active) {
+                idx = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+                if (idx < n) {
+                    pid = q.pid[idx];
+                    pos = q.rng[idx];
+                    tr.start(0, sc.n_ops, v3(q.ox[idx], q.oy[idx], q.oz[idx]), v3(q.dx[idx], q.dy[idx], q.dz[idx]), q.tm[idx], 0.001,
+                             RT_F64_MAX);
+                    active = true;
+                }
+            }
+            idle = __ballot_sync(0xffffffffu, !active);
+        }
+        if (idle == 0xffffffffu) break; /* no lane has a ray and none is left to fetch */
+#pragma unroll 1
+        for (int s = 0; s < RT_EXTEND_STEPS; ++s) {
+            if (active) {
+                tr.step<true>(ts, [&]() {
+                    rt_rng rng;
+                    path_rng(rng, wp, pid, pos);
+                    double u = rng.gen();
+                    pos = rng.pos;
+                    return u;
+                });
+                if (tr.done()) {
+                    hb.t[idx] = tr.best.t;
+                    hb.op[idx] = tr.best.op == RT_NO_HIT ? RT_NO_HIT : (tr.best.op | (tr.best.face << 29));
+                    q.rng[idx] = pos;
+                    active = false;
+                }
+            }
+        }
     }
 }
 
@@ -274,7 +321,7 @@ __global__ void __launch_bounds__(kThreads) k_trace_batch(DScene sc, const rtgpu
         r.tm = q.tm;
         rt_rng rng;
         rng.init(keys ? keys[i] : (uint64_t)i, 0, 0, RT_DOMAIN_BATCH, 0);
-        Closest c = closest_hit<true>(sc, 0, sc.n_ops, r.o, r.d, r.tm, q.t_min, q.t_max, &rng);
+        Closest c = closest_hit(sc, 0, sc.n_ops, r.o, r.d, r.tm, q.t_min, q.t_max, [&]() { return rng.gen(); });
         rtgpu_hit h;
         memset(&h, 0, sizeof h);
         h.gid = -1;
@@ -445,7 +492,7 @@ rtgpu_status ensure_wave(rtgpu_scene *s, size_t n_paths, int max_depth) {
         s->counts = nullptr;
         s->counts_host = nullptr;
         s->max_counts = max_depth + 2;
-        CK(cudaMalloc(&s->counts, sizeof(uint32_t) * (size_t)s->max_counts));
+        CK(cudaMalloc(&s->counts, 2 * sizeof(uint32_t) * (size_t)s->max_counts)); /* queue lengths, then fetch counters */
         CK(cudaMallocHost(&s->counts_host, sizeof(uint32_t) * (size_t)s->max_counts));
     }
     if (n_paths <= s->cap) return RTGPU_OK;
@@ -484,7 +531,7 @@ rtgpu_status run_wave(rtgpu_scene *s, const WaveParams &wp, int max_depth, cudaS
     rtgpu_status st = ensure_wave(s, wp.n_paths, max_depth);
     if (st != RTGPU_OK) return st;
     size_t n = wp.n_paths;
-    CK(cudaMemsetAsync(s->counts, 0, sizeof(uint32_t) * (size_t)s->max_counts, stream));
+    CK(cudaMemsetAsync(s->counts, 0, 2 * sizeof(uint32_t) * (size_t)s->max_counts, stream));
     CK(cudaMemcpyAsync(s->counts, &wp.n_paths, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
     CK(cudaMemsetAsync(s->cx, 0, n * 8, stream));
     CK(cudaMemsetAsync(s->cy, 0, n * 8, stream));
@@ -503,7 +550,7 @@ rtgpu_status run_wave(rtgpu_scene *s, const WaveParams &wp, int max_depth, cudaS
     if (timing) CK(cudaEventRecord(s->events[ev++], stream));
     for (int b = 0; b < max_depth; ++b) {
         PathQueue &qin = s->q[b & 1], &qout = s->q[(b + 1) & 1];
-        k_extend<<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->counts + b, wp);
+        k_extend<<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->counts + b, s->counts + s->max_counts + b, wp);
         if (timing) CK(cudaEventRecord(s->events[ev++], stream));
         k_shade<<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, qout, s->counts + b, s->counts + b + 1, s->cx, s->cy, s->cz,
                                                  want_len ? s->path_len : nullptr, wp, (uint32_t)b);

@@ -1,0 +1,188 @@
+"""CPU-side tests: host scene API, BVH build vs the oracle's restatement, lowering invariants,
+asset loaders, and that the C-ABI library loads and exports every symbol of include/rtgpu.h."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import rtb200 as rt
+from oracle_lib import OracleScene, make_rays
+
+D = rt.D
+ROOT = rt.REPO_ROOT
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "rtgpu.h")).read()
+    declared = set(re.findall(r"\b(rtgpu_[a-z_]+)\s*\(", hdr))
+    assert declared >= set(rt.GPU_SYMBOLS) and len(declared) == len(rt.GPU_SYMBOLS)
+    lib = C.CDLL(rt.GPU_LIB_PATH)  # loads without a GPU: cudart is linked statically
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.rtgpu_last_error.restype = C.c_char_p
+    assert isinstance(lib.rtgpu_last_error(), bytes)
+
+
+def test_cabi_rejects_bad_scenes_without_a_gpu():
+    G = rt.gpu_lib()
+    h = C.c_void_p()
+    desc = D.rtgpu_scene_desc()  # empty program: the reference panics on an empty BvhNode
+    assert G.rtgpu_scene_create(C.byref(desc), 0, C.byref(h)) == D.RTGPU_ERR_INVALID_SCENE
+    assert b"empty" in G.rtgpu_last_error()
+    s = rt.Scene(seed=1)
+    m = s.lambertian((0.5, 0.5, 0.5))
+    s.set_world(s.bvh_node([s.sphere((0, 0, 0), 1.0, m), s.sphere((3, 0, 0), 1.0, m)]))
+    lw = s.lower()
+    ops = (D.rtgpu_op * lw.desc.n_ops).from_address(C.addressof(lw.desc.ops.contents))
+    ops[0].skip = 0  # corrupt the skip link
+    assert G.rtgpu_scene_create(C.byref(lw.desc), 0, C.byref(h)) == D.RTGPU_ERR_INVALID_SCENE
+
+
+def test_struct_layouts_match_the_headers():
+    assert C.sizeof(D.rtgpu_op) == 64 and C.sizeof(D.rtgpu_xform) == 32 and C.sizeof(D.rtgpu_ctx) == 8
+    assert C.sizeof(D.rtgpu_material) == 40 and C.sizeof(D.rtgpu_texture) == 48 and C.sizeof(D.rtgpu_light) == 48
+    assert C.sizeof(D.rt_perlin) == 256 * 24 + 3 * 1024 and C.sizeof(D.rtgpu_ray) == 72 and C.sizeof(D.rtgpu_hit) == 104
+    assert C.sizeof(D.rt_object) == 16 + 96 and C.sizeof(D.rtgpu_camera) == 21 * 8
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 11, 400, 1000])
+def test_bvh_build_matches_oracle_restatement(n):
+    """host BvhNode::new_vec vs the oracle's own restatement: same stream -> same tree, same boxes"""
+    seed = 77
+    s = rt.Scene(seed=seed)
+    m = s.lambertian((0.5, 0.5, 0.5))
+    rng = np.random.default_rng(n)
+    ids = []
+    for i in range(n):
+        c = rng.uniform(-50, 50, 3)
+        if i % 3 == 0:
+            ids.append(s.moving_sphere(c, c + (0, rng.uniform(0, 2), 0), 0.0, 1.0, 1.0, m))
+        elif i % 3 == 1:
+            ids.append(s.sphere(c, rng.uniform(0.1, 3), m))
+        else:
+            ids.append(s.boxes(c, c + rng.uniform(0.1, 5, 3), m))
+    pos0 = s.rng_pos()
+    root = s.bvh_node(ids, 0.0, 1.0)
+    pos1 = s.rng_pos()
+    s.set_world(root)
+    orc = OracleScene(s)
+    listing_host, boxes_host = orc.bvh_listing(root)
+    listing_orc, boxes_orc, pos_after = orc.bvh_build(ids, 0.0, 1.0, seed, 0, pos0)
+    assert pos_after == pos1
+    assert np.array_equal(listing_host, listing_orc)
+    assert np.array_equal(boxes_host, boxes_orc)
+    assert int((listing_host == -1).sum()) <= pos1 - pos0  # one axis draw per node (+ zone rejections)
+
+
+def test_lowering_program_invariants():
+    s = rt.Scene(seed=2022).build_config("final_scene")
+    lw = s.lower()
+    ops = lw.ops()
+    kinds = ops["kind_ctx"] & 0xFF
+    n = len(ops)
+    i = 0
+    counts = {}
+    push = 0
+    while i < n:
+        k = int(kinds[i])
+        counts[k] = counts.get(k, 0) + 1
+        if k in (D.OP_NODE, D.OP_MEDIUM, D.OP_PUSH):
+            assert i < ops["skip"][i] <= n
+        push += (k == D.OP_PUSH) - (k == D.OP_POP)
+        assert push >= 0
+        i += 2 if k in (D.OP_MSPHERE, D.OP_TRI) else 1
+    assert push == 0
+    # TLAS 11 leaves (13 nodes) + 400 boxes (511 nodes) + 1000 spheres (1023 nodes), SURVEY.md 2.1
+    assert counts[D.OP_NODE] == 13 + 511 + 1023
+    assert counts[D.OP_BOX] >= 400 and counts[D.OP_MEDIUM] >= 2 and counts[D.OP_PUSH] == 1
+    assert counts[D.OP_SPHERE] >= 1000 + 5 + 2
+    assert lw.desc.n_lights == 1 and lw.desc.max_push_depth == 1
+    # singleton elision only drops repeated deterministic leaves
+    full = s.lower(elide_singletons=False)
+    assert full.desc.n_ops >= lw.desc.n_ops
+
+
+def test_scene_errors_mirror_reference_panics():
+    s = rt.Scene(seed=1)
+    with pytest.raises(rt.RtError, match="empty"):
+        s.bvh_node([])
+    with pytest.raises(rt.RtError):
+        s.image_texture("/nonexistent/earthmap.jpg")  # image::open(..).unwrap()
+    with pytest.raises(rt.RtError):
+        s.sphere((0, 0, 0), 1.0, 12345)
+    empty = s.hittable_list([])
+    with pytest.raises(rt.RtError, match="bounding box"):
+        s.bvh_node([empty, empty, empty])  # child without a box (bvh/mod.rs:76,79)
+
+
+def test_obj_loader_shuttle():
+    s = rt.Scene(seed=1)
+    m = s.lambertian((0.78, 0.78, 0.78))
+    ids = s.load_obj_triangles(os.path.join(rt.ASSET_DIR, "obj", "Shuttle.obj"), m)
+    assert len(ids) == 13079
+    g = s.graph()
+    tri0 = np.array(g.objects[ids[0]].p[:9])
+    # f 1 2 3 -> the first three `v` records, parsed as f32 and widened (scene.rs:386-388)
+    exp = np.array([0.00070933998, 0.25504929, -0.32778019, 0.014280531, 0.2465836, -0.19235966, 0.01427957, 0.25407809,
+                    -0.32796708], dtype=np.float32).astype(np.float64)
+    first_face = [ln for ln in open(os.path.join(rt.ASSET_DIR, "obj", "Shuttle.obj")) if ln.startswith("f ")][0].split()[1:]
+    if [int(t.split("/")[0]) for t in first_face] == [1, 2, 3]:
+        assert np.array_equal(tri0, exp)
+    allp = np.array([list(g.objects[i].p[:9]) for i in ids]).reshape(-1, 3)
+    assert np.array_equal(allp.astype(np.float32).astype(np.float64), allp)  # every coordinate is an f32 value
+    assert np.allclose(allp.min(axis=0), [-0.334, -0.0001, -0.475], atol=2e-3)
+    assert np.allclose(allp.max(axis=0), [0.335, 0.488, 0.545], atol=2e-3)
+    # 342 triangles lie in an x = const plane
+    tri = allp.reshape(-1, 3, 3)
+    assert int(((tri[:, 0, 0] == tri[:, 1, 0]) & (tri[:, 1, 0] == tri[:, 2, 0])).sum()) == 342
+
+
+def test_jpeg_decoder_against_libjpeg():
+    from PIL import Image
+    path = os.path.join(rt.ASSET_DIR, "earthmap.jpg")
+    mine = rt.decode_jpeg(path)
+    ref = np.asarray(Image.open(path).convert("RGB"))
+    assert mine.shape == ref.shape == (512, 1024, 3)
+    diff = np.abs(mine.astype(int) - ref.astype(int))
+    assert diff.max() <= 3 and diff.mean() < 0.3, (diff.max(), diff.mean())
+
+
+def test_image_texture_rows_are_stored_bottom_up():
+    s = rt.Scene(seed=1)
+    img = np.zeros((2, 2, 3), dtype=np.uint8)
+    img[0, 0] = (255, 0, 0)  # top-left of the file
+    img[1, 1] = (0, 0, 255)  # bottom-right
+    t = s.image_texture_rgb8(img)
+    s.set_world(s.sphere((0, 0, 0), 1.0, s.lambertian(t)))
+    orc = OracleScene(s)
+    # v = 0 is the BOTTOM row of the file (texture/mod.rs:96), no 1-v flip in value()
+    assert np.allclose(orc.texture_value(t, 0.9, 0.1, (0, 0, 0)), np.array([0, 0, 255]) / 255.999)
+    assert np.allclose(orc.texture_value(t, 0.1, 0.9, (0, 0, 0)), np.array([255, 0, 0]) / 255.999)
+    assert np.allclose(orc.texture_value(t, float("nan"), 2.0, (0, 0, 0)), np.array([255, 0, 0]) / 255.999)
+
+
+def test_config_scenes_build_and_lower():
+    for name, nobj in (("random_scene", 400), ("cornell_box", 6), ("final_scene", 1400), ("obj_cornell", 13079),
+                       ("cornell_smoke", 8), ("cornell_book3", 8)):
+        s = rt.Scene(seed=2022).build_config(name)
+        g = s.graph()
+        assert g.n_objects >= nobj and g.world >= 0
+        lw = s.lower()
+        assert lw.desc.n_ops > 0
+    # seeded: the same seed gives the same scene and tree, another seed a different one
+    a = rt.Scene(seed=5).build_config("random_scene").lower().ops()
+    b = rt.Scene(seed=5).build_config("random_scene").lower().ops()
+    c = rt.Scene(seed=6).build_config("random_scene").lower().ops()
+    assert np.array_equal(a, b) and (len(a) != len(c) or not np.array_equal(a, c))
+
+
+def test_oracle_image_statistics_are_stable_across_seeds():
+    """The oracle is a Monte-Carlo estimator: two disjoint sample sets agree within noise."""
+    s = rt.Scene(seed=2022).build_config("cornell_box")
+    orc = OracleScene(s)
+    a, _ = orc.render(24, 24, 0, 64, threads=4)
+    b, _ = orc.render(24, 24, 64, 128, threads=4)
+    ma, mb = a.mean() / 64, b.mean() / 64
+    assert abs(ma - mb) / ma < 0.1
