@@ -224,20 +224,44 @@ __device__ __forceinline__ void ray_state_derive(RayState &r) {
     r.sg.z = r.inv.z < 0.;
 }
 
-struct Traversal;
 __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm,
                                                      double tmin, double tmax);
 
-/* Resumable walk: start(), then step() until done().  One step = a run of NODE ops + one leaf. */
+/* phases of the warp scheduler: ops whose code is the same run together */
+enum { PH_NODE = 0, PH_SPHERE = 1, PH_BOX = 2, PH_TRI = 3, PH_MISC = 4, PH_COUNT = 5, PH_NONE = 7 };
+__device__ __forceinline__ uint32_t phase_of_kind(uint32_t kind) {
+    /* NODE SPHERE MSPHERE RECT_XY RECT_XZ RECT_YZ BOX TRI MEDIUM PUSH POP, 3 bits each */
+    return (uint32_t)((044432444110ull >> (3 * kind)) & 7ull);
+}
+
+struct SavedRays {
+    double v[RT_MAX_PUSH][6];
+};
+
+/* Resumable in-order walk of ops [begin, end).  The current op (header + payload, 64 B = four
+ * 128-bit loads issued together) is fetched as soon as the index is known; exec_*() consume it.
+ * One call of exec handles one op, so a warp can run "all lanes that sit on a NODE" together,
+ * then "all lanes that sit on a sphere", ... (see extend_warp_loop). */
 struct Traversal {
     RayState r;
     double tm, tmin;
     Closest best;
     uint32_t i, end;
     int sp;
-    V3 saved_o[RT_MAX_PUSH], saved_d[RT_MAX_PUSH];
+    uint4 h;     /* header of op i */
+    double p[6]; /* payload of op i */
+    /* the PUSH/POP stack lives OUTSIDE this struct (SavedRays): it is indexed dynamically, and an
+     * aggregate with a dynamically indexed member is kept in local memory as a whole */
 
-    __device__ __forceinline__ void start(uint32_t begin, uint32_t end_, V3 o, V3 d, double tm_, double tmin_, double tmax) {
+    __device__ __forceinline__ void fetch_op(const TravScene sc) {
+        if (i < end) {
+            const rtgpu_op *op = sc.ops + i;
+            h = load_op_header(op);
+            load_op_payload(op, p);
+        }
+    }
+    __device__ __forceinline__ void start(const TravScene sc, uint32_t begin, uint32_t end_, V3 o, V3 d, double tm_, double tmin_,
+                                          double tmax) {
         best.t = tmax;
         best.op = RT_NO_HIT;
         best.face = 0;
@@ -249,55 +273,46 @@ struct Traversal {
         i = begin;
         end = end_;
         sp = 0;
+        fetch_op(sc);
     }
     __device__ __forceinline__ bool done() const { return i >= end; }
+    __device__ __forceinline__ uint32_t phase() const { return phase_of_kind(h.x & 0xffu); }
 
-    /* DRAW() returns the next uniform of the ray's stream (ConstantMedium free path) */
+    __device__ __forceinline__ void exec_node(const TravScene sc) {
+        i = hit_aabb(r.o, r.inv, r.sg, p, tmin, best.t) ? i + 1 : h.y;
+        fetch_op(sc);
+    }
+    __device__ __forceinline__ void exec_sphere(const TravScene sc) {
+        V3 c = v3(p[0], p[1], p[2]);
+        uint32_t width = 1;
+        if ((h.x & 0xffu) == RTGPU_OP_MSPHERE) { /* MovingSphere::center, sphere.rs:124-127 */
+            double q[8];
+            load_slot8(sc.ops + i + 1, q);
+            c = c + (v3(q[0], q[1], q[2]) - c) * ((tm - p[4]) / (p[5] - p[4]));
+            width = 2;
+        }
+        if (hit_sphere(r.o, r.d, r.a, c, p[3], tmin, best.t)) best.op = i;
+        i += width;
+        fetch_op(sc);
+    }
+    __device__ __forceinline__ void exec_box(const TravScene sc) {
+        if (hit_box(r.o, r.d, p, tmin, best.t, best.face)) best.op = i;
+        i += 1;
+        fetch_op(sc);
+    }
+    __device__ __forceinline__ void exec_tri(const TravScene sc) {
+        double q[8];
+        load_slot8(sc.ops + i + 1, q);
+        if (hit_triangle(r.o, r.d, v3(p[0], p[1], p[2]), v3(p[3], p[4], p[5]), v3(q[0], q[1], q[2]), v3(q[3], q[4], q[5]), tmin,
+                         best.t))
+            best.op = i;
+        i += 2;
+        fetch_op(sc);
+    }
+    /* rects, ConstantMedium, PUSH, POP.  DRAW() = next uniform of the ray's stream */
     template <bool MAIN, typename DRAW>
-    __device__ __forceinline__ void step(const TravScene sc, DRAW &&draw) {
-        const rtgpu_op *op = sc.ops + i;
-        uint4 h = load_op_header(op);
-        uint32_t kind = h.x & 0xffu;
-        double p[6];
-        /* ---- run of BvhNode boxes ---- */
-        while (kind == RTGPU_OP_NODE) {
-            load_op_payload(op, p);
-            i = hit_aabb(r.o, r.inv, r.sg, p, tmin, best.t) ? i + 1 : h.y;
-            if (i >= end) return;
-            op = sc.ops + i;
-            h = load_op_header(op);
-            kind = h.x & 0xffu;
-        }
-        /* ---- one leaf / control op ---- */
-        if (kind != RTGPU_OP_POP) load_op_payload(op, p);
-        switch (kind) {
-        case RTGPU_OP_SPHERE:
-            if (hit_sphere(r.o, r.d, r.a, v3(p[0], p[1], p[2]), p[3], tmin, best.t)) best.op = i;
-            i += 1;
-            break;
-        case RTGPU_OP_BOX:
-            if (hit_box(r.o, r.d, p, tmin, best.t, best.face)) best.op = i;
-            i += 1;
-            break;
-        case RTGPU_OP_TRI: {
-            double q[8];
-            load_slot8(op + 1, q);
-            if (hit_triangle(r.o, r.d, v3(p[0], p[1], p[2]), v3(p[3], p[4], p[5]), v3(q[0], q[1], q[2]), v3(q[3], q[4], q[5]),
-                             tmin, best.t))
-                best.op = i;
-            i += 2;
-            break;
-        }
-        case RTGPU_OP_MSPHERE: {
-            double q[8];
-            load_slot8(op + 1, q);
-            /* MovingSphere::center, sphere.rs:124-127 */
-            V3 c0 = v3(p[0], p[1], p[2]), c1 = v3(q[0], q[1], q[2]);
-            V3 c = c0 + (c1 - c0) * ((tm - p[4]) / (p[5] - p[4]));
-            if (hit_sphere(r.o, r.d, r.a, c, p[3], tmin, best.t)) best.op = i;
-            i += 2;
-            break;
-        }
+    __device__ __forceinline__ void exec_misc(const TravScene sc, SavedRays &stk, DRAW &&draw) {
+        switch (h.x & 0xffu) {
         case RTGPU_OP_RECT_XY:
             if (hit_rect<2>(r.o, r.d, p[0], p[1], p[2], p[3], p[4], tmin, best.t)) best.op = i;
             i += 1;
@@ -315,10 +330,10 @@ struct Traversal {
                 double t1 = CUDART_INF, t2 = CUDART_INF;
                 bool h1, h2 = false;
                 bool single_sphere = h.y == i + 2;
-                if (single_sphere) single_sphere = (load_op_header(op + 1).x & 0xffu) == RTGPU_OP_SPHERE;
+                if (single_sphere) single_sphere = (load_op_header(sc.ops + i + 1).x & 0xffu) == RTGPU_OP_SPHERE;
                 if (single_sphere) { /* boundary = one Sphere (both media of final_scene) */
                     double bp[6];
-                    load_op_payload(op + 1, bp);
+                    load_op_payload(sc.ops + i + 1, bp);
                     V3 c = v3(bp[0], bp[1], bp[2]);
                     h1 = hit_sphere(r.o, r.d, r.a, c, bp[3], -CUDART_INF, t1);
                     if (h1) h2 = hit_sphere(r.o, r.d, r.a, c, bp[3], t1 + 0.0001, t2);
@@ -351,8 +366,8 @@ struct Traversal {
             i = h.y;
             break;
         case RTGPU_OP_PUSH: {
-            saved_o[sp] = r.o;
-            saved_d[sp] = r.d;
+            stk.v[sp][0] = r.o.x; stk.v[sp][1] = r.o.y; stk.v[sp][2] = r.o.z;
+            stk.v[sp][3] = r.d.x; stk.v[sp][4] = r.d.y; stk.v[sp][5] = r.d.z;
             ++sp;
             for (uint32_t j = 0; j < h.w; ++j) {
                 rtgpu_xform xf = load_xform(sc, h.z + j);
@@ -364,11 +379,23 @@ struct Traversal {
         }
         default: /* POP */
             --sp;
-            r.o = saved_o[sp];
-            r.d = saved_d[sp];
+            r.o = v3(stk.v[sp][0], stk.v[sp][1], stk.v[sp][2]);
+            r.d = v3(stk.v[sp][3], stk.v[sp][4], stk.v[sp][5]);
             ray_state_derive(r);
             i += 1;
             break;
+        }
+        fetch_op(sc);
+    }
+    /* one op, whatever it is (single-ray loops) */
+    template <bool MAIN, typename DRAW>
+    __device__ __forceinline__ void step(const TravScene sc, SavedRays &stk, DRAW &&draw) {
+        switch (phase()) {
+        case PH_NODE: exec_node(sc); break;
+        case PH_SPHERE: exec_sphere(sc); break;
+        case PH_BOX: exec_box(sc); break;
+        case PH_TRI: exec_tri(sc); break;
+        default: exec_misc<MAIN>(sc, stk, draw); break;
         }
     }
 };
@@ -377,20 +404,101 @@ struct Traversal {
 __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm,
                                                      double tmin, double tmax) {
     Traversal tr;
-    tr.start(begin, end, o, d, tm, tmin, tmax);
-    while (!tr.done()) tr.step<false>(sc, []() { return 0.; });
+    SavedRays stk;
+    tr.start(sc, begin, end, o, d, tm, tmin, tmax);
+    while (!tr.done()) tr.step<false>(sc, stk, []() { return 0.; });
     return tr.best;
 }
 
-/* closest hit of one ray, run to completion (dumped batches, light probes) */
-template <typename DRAW>
-__device__ __forceinline__ Closest closest_hit(const DScene &sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm, double tmin,
-                                               double tmax, DRAW &&draw) {
+#ifndef RT_EXTEND_REFILL
+#define RT_EXTEND_REFILL 8 /* refill when at least this many lanes of the warp are idle */
+#endif
+#ifndef RT_NODE_QUORUM_PCT
+#define RT_NODE_QUORUM_PCT 25 /* keep running NODE rounds while at least this share of the live lanes sits on a NODE */
+#endif
+
+/* The extend loop of one warp (persistent): every lane owns one ray at a time.
+ *  - dynamic fetch: a lane whose ray is finished takes the next ray index from a global counter
+ *    (one atomic per refill of the warp), so trip-count differences do not idle lanes;
+ *  - phase voting: each round the warp runs only the kind of op most lanes are waiting on
+ *    (NODE / sphere / box / triangle / misc), so the instructions that are issued carry many
+ *    active lanes instead of the 6-8 of 32 that plain SIMT divergence leaves.
+ * Each ray still executes its own ops strictly in program order with its own running best, so
+ * results are identical to the sequential walk.
+ * IO: load(idx, o, d, tm, tmin, tmax), draw() -> next uniform of the current ray, store(idx, Closest). */
+#ifdef RT_DEBUG_COUNTERS
+__device__ unsigned long long g_dbg[16]; /* [k] rounds that picked phase k, [8+k] lanes that ran in them */
+#endif
+template <typename IO>
+__device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_ops, uint32_t n, uint32_t *fetch, IO &io) {
+    const uint32_t lane = threadIdx.x & 31u;
     Traversal tr;
-    tr.start(begin, end, o, d, tm, tmin, tmax);
-    TravScene ts = trav_of(sc);
-    while (!tr.done()) tr.step<true>(ts, draw);
-    return tr.best;
+    SavedRays stk;
+    bool active = false, exhausted = false;
+    uint32_t idx = 0;
+    for (;;) {
+        uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= RT_EXTEND_REFILL)) {
+            int leader = __ffs(idle) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(fetch, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            exhausted = base + (uint32_t)__popc(idle) >= n;
+            if (!active) {
+                idx = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+                if (idx < n) {
+                    V3 o, d;
+                    double tm, tmin, tmax;
+                    io.load(idx, o, d, tm, tmin, tmax);
+                    tr.start(ts, 0, n_ops, o, d, tm, tmin, tmax);
+                    active = !tr.done();
+                    if (!active) io.store(idx, tr.best);
+                }
+            }
+            idle = __ballot_sync(0xffffffffu, !active);
+        }
+        if (idle == 0xffffffffu) break; /* no lane has a ray and none is left to fetch */
+        /* NODE rounds: as long as enough lanes sit on a BvhNode box, run only those (uniform code,
+         * one ballot of overhead); lanes that reached a leaf wait.  Then every waiting lane runs its
+         * leaf op once (plain SIMT over the few leaf kinds) and the cycle repeats. */
+        const uint32_t n_active = 32u - (uint32_t)__popc(idle);
+        const uint32_t node_quorum = max(1u, (n_active * RT_NODE_QUORUM_PCT) / 100u);
+#pragma unroll 1
+        for (;;) {
+            bool in_node = active && tr.phase() == PH_NODE;
+            uint32_t m = __ballot_sync(0xffffffffu, in_node);
+#ifdef RT_DEBUG_COUNTERS
+            if (lane == 0 && (uint32_t)__popc(m) >= node_quorum) {
+                atomicAdd(&g_dbg[0], 1ull);
+                atomicAdd(&g_dbg[8], (unsigned long long)__popc(m));
+            }
+#endif
+            if ((uint32_t)__popc(m) < node_quorum) break;
+            if (in_node) {
+                tr.exec_node(ts);
+                if (tr.done()) {
+                    io.store(idx, tr.best);
+                    active = false;
+                }
+            }
+        }
+        if (active) {
+#ifdef RT_DEBUG_COUNTERS
+            atomicAdd(&g_dbg[tr.phase()], 1ull);
+#endif
+            switch (tr.phase()) {
+            case PH_NODE: break; /* below the quorum: waits for the next NODE rounds */
+            case PH_SPHERE: tr.exec_sphere(ts); break;
+            case PH_BOX: tr.exec_box(ts); break;
+            case PH_TRI: tr.exec_tri(ts); break;
+            default: tr.exec_misc<true>(ts, stk, [&]() { return io.draw(); }); break;
+            }
+            if (tr.done()) {
+                io.store(idx, tr.best);
+                active = false;
+            }
+        }
+    }
 }
 
 /* ---- HitRecord of the winner (hittable/mod.rs:18-57), rebuilt once per ray ------------------- */

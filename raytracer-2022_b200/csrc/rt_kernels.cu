@@ -17,10 +17,14 @@
  * Randomness: one Philox slot stream per path, keyed (seed, pixel, sample) -- include/rt_rng.h.
  */
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
 
 #include "rt_device.cuh"
 
@@ -99,67 +103,45 @@ __global__ void __launch_bounds__(kThreads) k_raygen(DScene sc, PathQueue q, Wav
     }
 }
 
-/* world.hit(r, 0.001, f64::MAX), main.rs:243 -- persistent warps with dynamic ray fetch.
- * Rays of one warp need very different numbers of traversal steps; a lane whose ray is finished
- * takes the next ray index from a global counter (one atomic per warp refill) instead of idling
- * until the slowest lane is done. */
+/* world.hit(r, 0.001, f64::MAX), main.rs:243 -- persistent warps, see extend_warp_loop */
 #ifndef RT_EXTEND_MIN_BLOCKS
 #define RT_EXTEND_MIN_BLOCKS 4
 #endif
-#ifndef RT_EXTEND_REFILL
-#define RT_EXTEND_REFILL 8 /* refill when at least this many lanes are idle */
-#endif
-#ifndef RT_EXTEND_STEPS
-#define RT_EXTEND_STEPS 4 /* traversal steps between two refill checks */
-#endif
+struct QueueIO {
+    PathQueue q;
+    HitBuf hb;
+    WaveParams wp;
+    uint32_t pid, pos, cur;
+    __device__ __forceinline__ void load(uint32_t idx, V3 &o, V3 &d, double &tm, double &tmin, double &tmax) {
+        o = v3(q.ox[idx], q.oy[idx], q.oz[idx]);
+        d = v3(q.dx[idx], q.dy[idx], q.dz[idx]);
+        tm = q.tm[idx];
+        tmin = 0.001;
+        tmax = RT_F64_MAX;
+        pid = q.pid[idx];
+        pos = q.rng[idx];
+        cur = idx;
+    }
+    __device__ __forceinline__ double draw() { /* the path's stream resumes at slot `pos` */
+        rt_rng rng;
+        path_rng(rng, wp, pid, pos);
+        double u = rng.gen();
+        pos = rng.pos;
+        return u;
+    }
+    __device__ __forceinline__ void store(uint32_t idx, const Closest &c) {
+        hb.t[idx] = c.t;
+        hb.op[idx] = c.op == RT_NO_HIT ? RT_NO_HIT : (c.op | (c.face << 29));
+        q.rng[idx] = pos;
+    }
+};
 __global__ void __launch_bounds__(kThreads, RT_EXTEND_MIN_BLOCKS) k_extend(DScene sc, PathQueue q, HitBuf hb, const uint32_t *count,
                                                                            uint32_t *fetch, WaveParams wp) {
-    const uint32_t n = *count;
-    const uint32_t lane = threadIdx.x & 31u;
-    const TravScene ts = trav_of(sc);
-    Traversal tr;
-    bool active = false, exhausted = false;
-    uint32_t idx = 0, pid = 0, pos = 0;
-    for (;;) {
-        uint32_t idle = __ballot_sync(0xffffffffu, !active);
-        if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= RT_EXTEND_REFILL)) {
-            int leader = __ffs(idle) - 1;
-            uint32_t base = 0;
-            if ((int)lane == leader) base = atomicAdd(fetch, (uint32_t)__popc(idle));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            exhausted = base + (uint32_t)__popc(idle) >= n;
-            if (!active) {
-                idx = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
-                if (idx < n) {
-                    pid = q.pid[idx];
-                    pos = q.rng[idx];
-                    tr.start(0, sc.n_ops, v3(q.ox[idx], q.oy[idx], q.oz[idx]), v3(q.dx[idx], q.dy[idx], q.dz[idx]), q.tm[idx], 0.001,
-                             RT_F64_MAX);
-                    active = true;
-                }
-            }
-            idle = __ballot_sync(0xffffffffu, !active);
-        }
-        if (idle == 0xffffffffu) break; /* no lane has a ray and none is left to fetch */
-#pragma unroll 1
-        for (int s = 0; s < RT_EXTEND_STEPS; ++s) {
-            if (active) {
-                tr.step<true>(ts, [&]() {
-                    rt_rng rng;
-                    path_rng(rng, wp, pid, pos);
-                    double u = rng.gen();
-                    pos = rng.pos;
-                    return u;
-                });
-                if (tr.done()) {
-                    hb.t[idx] = tr.best.t;
-                    hb.op[idx] = tr.best.op == RT_NO_HIT ? RT_NO_HIT : (tr.best.op | (tr.best.face << 29));
-                    q.rng[idx] = pos;
-                    active = false;
-                }
-            }
-        }
-    }
+    QueueIO io;
+    io.q = q;
+    io.hb = hb;
+    io.wp = wp;
+    extend_warp_loop(trav_of(sc), sc.n_ops, *count, fetch, io);
 }
 
 /* the body of ray_color (main.rs:233-278) for one segment; returns true when the path goes on */
@@ -290,6 +272,102 @@ __global__ void __launch_bounds__(kThreads) k_shade(DScene sc, PathQueue qin, Hi
     }
 }
 
+/* ---- ray reordering between bounces: rays that start close together and point the same way walk
+ * nearly the same ops in the same order (the traversal order is ray-independent), so a warp of
+ * neighbours in the sorted queue diverges far less.  key = Morton(origin, 7 bits/axis) : direction
+ * (octant + 2 x 3 bits). ------------------------------------------------------------------------ */
+__device__ __forceinline__ uint32_t f2ord(float f) { /* order-preserving float -> uint */
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+/* robust origin bounds: mean +- 2.5 sigma per axis (a ConstantMedium as large as the world scatters a few
+ * rays very far away; min/max bounds would waste the key bits on empty space) */
+__global__ void k_sort_bounds(PathQueue q, const uint32_t *count, double *moments /* sum xyz, sum xyz^2, n */) {
+    uint32_t n = *count;
+    double s1[3] = {0., 0., 0.}, s2[3] = {0., 0., 0.}, cnt = 0.;
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride * 4) { /* every 4th stripe: a sample is enough */
+        double x = q.ox[i], y = q.oy[i], z = q.oz[i];
+        if (fabs(x) < 1e30 && fabs(y) < 1e30 && fabs(z) < 1e30) {
+            s1[0] += x; s1[1] += y; s1[2] += z;
+            s2[0] += x * x; s2[1] += y * y; s2[2] += z * z;
+            cnt += 1.;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        for (int c = 0; c < 3; ++c) {
+            s1[c] += __shfl_xor_sync(0xffffffffu, s1[c], o);
+            s2[c] += __shfl_xor_sync(0xffffffffu, s2[c], o);
+        }
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0 && cnt > 0.) {
+        for (int c = 0; c < 3; ++c) {
+            atomicAdd(moments + c, s1[c]);
+            atomicAdd(moments + 3 + c, s2[c]);
+        }
+        atomicAdd(moments + 6, cnt);
+    }
+}
+__device__ __forceinline__ uint32_t spread7(uint32_t v) { /* 7 bits -> every third bit */
+    uint32_t r = 0;
+#pragma unroll
+    for (int b = 0; b < 7; ++b) r |= ((v >> b) & 1u) << (3 * b);
+    return r;
+}
+__global__ void k_sort_keys(PathQueue q, const uint32_t *count, const double *moments, uint32_t *keys, uint32_t *idx, uint32_t n_pad) {
+    uint32_t n = *count;
+    float lo[3], inv[3];
+    for (int c = 0; c < 3; ++c) {
+        double cnt = fmax(moments[6], 1.);
+        double mean = moments[c] / cnt;
+        double var = fmax(moments[3 + c] / cnt - mean * mean, 0.);
+        double sd = sqrt(var);
+        lo[c] = (float)(mean - 2.5 * sd);
+        float ext = (float)(5.0 * sd);
+        inv[c] = ext > 0.f ? 127.999f / ext : 0.f;
+    }
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+        uint32_t key = 0xffffffffu;
+        if (i < n) {
+            float o[3] = {(float)q.ox[i], (float)q.oy[i], (float)q.oz[i]};
+            float d[3] = {(float)q.dx[i], (float)q.dy[i], (float)q.dz[i]};
+            uint32_t cell[3];
+            for (int c = 0; c < 3; ++c) {
+                float t = (o[c] - lo[c]) * inv[c];
+                cell[c] = (uint32_t)fminf(fmaxf(t, 0.f), 127.f);
+            }
+            uint32_t morton = spread7(cell[0]) | (spread7(cell[1]) << 1) | (spread7(cell[2]) << 2);
+            uint32_t oct = (d[0] < 0.f ? 1u : 0u) | (d[1] < 0.f ? 2u : 0u) | (d[2] < 0.f ? 4u : 0u);
+            float ax = fabsf(d[0]), ay = fabsf(d[1]), az = fabsf(d[2]);
+            float m = fmaxf(ax, fmaxf(ay, az));
+            float s = m > 0.f ? 7.999f / m : 0.f;
+            uint32_t major = (ax >= ay && ax >= az) ? 0u : (ay >= az ? 1u : 2u);
+            float u = major == 0 ? ay : ax, v = major == 2 ? ay : az;
+            uint32_t dq = (major << 6) | ((uint32_t)(u * s) << 3) | (uint32_t)(v * s); /* 2 + 3 + 3 bits */
+            key = (morton << 11) | (oct << 8) | dq;
+            key &= 0x7fffffffu;
+        }
+        keys[i] = key;
+        idx[i] = i;
+    }
+}
+__global__ void k_sort_gather(PathQueue src, PathQueue dst, const uint32_t *count, const uint32_t *idx) {
+    uint32_t n = *count;
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        uint32_t i = idx[j];
+        dst.ox[j] = src.ox[i]; dst.oy[j] = src.oy[i]; dst.oz[j] = src.oz[i];
+        dst.dx[j] = src.dx[i]; dst.dy[j] = src.dy[i]; dst.dz[j] = src.dz[i];
+        dst.tm[j] = src.tm[i];
+        dst.bx[j] = src.bx[i]; dst.by[j] = src.by[i]; dst.bz[j] = src.bz[i];
+        dst.pid[j] = src.pid[i];
+        dst.rng[j] = src.rng[i];
+    }
+}
+
 /* pixel_color += ray_color(...) over the wave's samples, in sample order (main.rs:144-151) */
 __global__ void k_accumulate(const double *cx, const double *cy, const double *cz, float *accum, uint32_t npix, uint32_t nsamples,
                              int add) {
@@ -310,27 +388,58 @@ __global__ void k_accumulate(const double *cx, const double *cy, const double *c
     }
 }
 
-/* dumped-ray batch: BvhNode::hit + the record of the winner */
-__global__ void __launch_bounds__(kThreads) k_trace_batch(DScene sc, const rtgpu_ray *rays, const uint64_t *keys, rtgpu_hit *out, int64_t n) {
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+/* dumped-ray batch: BvhNode::hit through the SAME warp loop as k_extend, then the record of the winner */
+struct BatchIO {
+    const rtgpu_ray *rays;
+    const uint64_t *keys;
+    double *t;
+    uint32_t *op, *rng_pos;
+    rt_rng rng;
+    __device__ __forceinline__ void load(uint32_t idx, V3 &o, V3 &d, double &tm, double &tmin, double &tmax) {
+        rtgpu_ray q = rays[idx];
+        o = v3(q.o[0], q.o[1], q.o[2]);
+        d = v3(q.d[0], q.d[1], q.d[2]);
+        tm = q.tm;
+        tmin = q.t_min;
+        tmax = q.t_max;
+        rng.init(keys ? keys[idx] : (uint64_t)idx, 0, 0, RT_DOMAIN_BATCH, 0);
+    }
+    __device__ __forceinline__ double draw() { return rng.gen(); }
+    __device__ __forceinline__ void store(uint32_t idx, const Closest &c) {
+        t[idx] = c.t;
+        op[idx] = c.op == RT_NO_HIT ? RT_NO_HIT : (c.op | (c.face << 29));
+        rng_pos[idx] = rng.pos;
+    }
+};
+__global__ void __launch_bounds__(kThreads, RT_EXTEND_MIN_BLOCKS) k_trace_extend(DScene sc, const rtgpu_ray *rays, const uint64_t *keys,
+                                                                                 double *t, uint32_t *op, uint32_t *rng_pos, uint32_t n,
+                                                                                 uint32_t *fetch) {
+    BatchIO io;
+    io.rays = rays;
+    io.keys = keys;
+    io.t = t;
+    io.op = op;
+    io.rng_pos = rng_pos;
+    extend_warp_loop(trav_of(sc), sc.n_ops, n, fetch, io);
+}
+__global__ void __launch_bounds__(kThreads) k_trace_record(DScene sc, const rtgpu_ray *rays, const double *t, const uint32_t *op,
+                                                           const uint32_t *rng_pos, rtgpu_hit *out, uint32_t n) {
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         rtgpu_ray q = rays[i];
         Ray r;
         r.o = v3(q.o[0], q.o[1], q.o[2]);
         r.d = v3(q.d[0], q.d[1], q.d[2]);
         r.tm = q.tm;
-        rt_rng rng;
-        rng.init(keys ? keys[i] : (uint64_t)i, 0, 0, RT_DOMAIN_BATCH, 0);
-        Closest c = closest_hit(sc, 0, sc.n_ops, r.o, r.d, r.tm, q.t_min, q.t_max, [&]() { return rng.gen(); });
         rtgpu_hit h;
         memset(&h, 0, sizeof h);
         h.gid = -1;
         h.inst = -1;
         h.mat = -1;
-        h.rng_pos = rng.pos;
-        if (c.op != RT_NO_HIT) {
+        h.rng_pos = rng_pos[i];
+        if (op[i] != RT_NO_HIT) {
             HitRec rec;
-            make_record(sc, r, c.t, c.op, c.face, rec);
+            make_record(sc, r, t[i], op[i] & 0x1fffffffu, op[i] >> 29, rec);
             h.hit = 1;
             h.t = rec.t;
             h.p[0] = rec.p.x; h.p[1] = rec.p.y; h.p[2] = rec.p.z;
@@ -384,24 +493,52 @@ __global__ void k_resolve(const float *accum, int w, int h, int spp, uint8_t *rg
 } // namespace
 
 /* --------------------------------------------------------------------------------------------- */
-struct rtgpu_scene {
-    int device = 0;
-    DScene d;
-    std::vector<void *> allocs;
-    /* wave buffers, grown on demand */
+/* per-device working memory of the wavefront: queues, hit buffer, contributions, counters.  It is
+ * independent of the scene, so a destroyed scene parks it for the next scene on the same device
+ * (an application that re-creates its scene every frame does not pay cudaMalloc of GBs each time). */
+struct WaveRes {
     size_t cap = 0;
     void *wave_mem = nullptr;
     PathQueue q[2];
     HitBuf hb;
     double *cx = nullptr, *cy = nullptr, *cz = nullptr;
     uint32_t *path_len = nullptr;
-    uint32_t *counts = nullptr;      /* device, RTGPU_MAX_BOUNCE_STATS*4 + ... */
+    uint32_t *counts = nullptr;      /* device: queue length per bounce, then the fetch counters */
     uint32_t *counts_host = nullptr; /* pinned */
     int max_counts = 0;
     float *accum_dev = nullptr;
     size_t accum_cap = 0;
     std::vector<cudaEvent_t> events;
+    /* ray reordering */
+    uint32_t *sort_keys[2] = {nullptr, nullptr}, *sort_idx[2] = {nullptr, nullptr};
+    double *sort_bounds = nullptr;
+    void *sort_temp = nullptr;
+    size_t sort_temp_bytes = 0;
+    void release() {
+        if (wave_mem) cudaFree(wave_mem);
+        if (counts) cudaFree(counts);
+        if (counts_host) cudaFreeHost(counts_host);
+        if (accum_dev) cudaFree(accum_dev);
+        if (sort_temp) cudaFree(sort_temp);
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+        *this = WaveRes();
+    }
 };
+
+struct rtgpu_scene : WaveRes {
+    int device = 0;
+    DScene d;
+    std::vector<void *> allocs;
+    int sort_mode = 0; /* RTGPU_SORT_RAYS=1: reorder rays between bounces */
+    uint32_t sort_min = 1u << 16;
+};
+
+namespace {
+constexpr int kMaxDevices = 64;
+std::mutex g_park_mutex;
+WaveRes g_parked[kMaxDevices];
+bool g_parked_valid[kMaxDevices];
+} // namespace
 
 namespace {
 
@@ -501,7 +638,7 @@ rtgpu_status ensure_wave(rtgpu_scene *s, size_t n_paths, int max_depth) {
     s->cap = 0;
     size_t n = (n_paths + 255) & ~(size_t)255;
     /* per path: 2 queues x (10 doubles + 2 u32) + hit (double + u32) + contrib (3 doubles) + path_len */
-    size_t bytes = n * (2 * (10 * 8 + 2 * 4) + 8 + 4 + 3 * 8 + 4);
+    size_t bytes = n * (2 * (10 * 8 + 2 * 4) + 8 + 4 + 3 * 8 + 4 + 4 * 4) + 256;
     CK(cudaMalloc(&s->wave_mem, bytes));
     char *p = static_cast<char *>(s->wave_mem);
     auto take_d = [&](double *&dst) { dst = reinterpret_cast<double *>(p); p += n * 8; };
@@ -516,6 +653,19 @@ rtgpu_status ensure_wave(rtgpu_scene *s, size_t n_paths, int max_depth) {
     for (int k = 0; k < 2; ++k) { take_u(s->q[k].pid); take_u(s->q[k].rng); }
     take_u(s->hb.op);
     take_u(s->path_len);
+    take_u(s->sort_keys[0]); take_u(s->sort_keys[1]); take_u(s->sort_idx[0]); take_u(s->sort_idx[1]);
+    s->sort_bounds = reinterpret_cast<double *>(p + ((8 - ((size_t)p & 7)) & 7));
+    {
+        size_t need = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, need, s->sort_keys[0], s->sort_keys[1], s->sort_idx[0], s->sort_idx[1], (int)n, 0, 31);
+        if (need > s->sort_temp_bytes) {
+            if (s->sort_temp) cudaFree(s->sort_temp);
+            s->sort_temp = nullptr;
+            s->sort_temp_bytes = 0;
+            CK(cudaMalloc(&s->sort_temp, need));
+            s->sort_temp_bytes = need;
+        }
+    }
     s->cap = n;
     return RTGPU_OK;
 }
@@ -537,7 +687,7 @@ rtgpu_status run_wave(rtgpu_scene *s, const WaveParams &wp, int max_depth, cudaS
     CK(cudaMemsetAsync(s->cy, 0, n * 8, stream));
     CK(cudaMemsetAsync(s->cz, 0, n * 8, stream));
     if (want_len) CK(cudaMemsetAsync(s->path_len, 0, n * 4, stream));
-    size_t n_ev = timing ? (size_t)(2 * max_depth + 2) : 0;
+    size_t n_ev = timing ? (size_t)(3 * max_depth + 2) : 0;
     while (s->events.size() < n_ev) {
         cudaEvent_t e;
         CK(cudaEventCreate(&e));
@@ -548,32 +698,59 @@ rtgpu_status run_wave(rtgpu_scene *s, const WaveParams &wp, int max_depth, cudaS
     if (timing) CK(cudaEventRecord(s->events[ev++], stream));
     k_raygen<<<blocks, kThreads, 0, stream>>>(s->d, s->q[0], wp);
     if (timing) CK(cudaEventRecord(s->events[ev++], stream));
+    int cur = 0; /* queue that holds the rays of the current bounce */
+    int bounces_run = 0;
     for (int b = 0; b < max_depth; ++b) {
-        PathQueue &qin = s->q[b & 1], &qout = s->q[(b + 1) & 1];
+        if (s->sort_mode && b >= 1) {
+            /* the queue length is needed on the host to size the sort (one small readback per bounce) */
+            CK(cudaMemcpyAsync(s->counts_host + b, s->counts + b, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            uint32_t nb = s->counts_host[b];
+            if (nb == 0) break;
+            if (nb >= s->sort_min) {
+                CK(cudaMemsetAsync(s->sort_bounds, 0, 7 * sizeof(double), stream));
+                k_sort_bounds<<<blocks, kThreads, 0, stream>>>(s->q[cur], s->counts + b, s->sort_bounds);
+                k_sort_keys<<<blocks, kThreads, 0, stream>>>(s->q[cur], s->counts + b, s->sort_bounds, s->sort_keys[0], s->sort_idx[0], nb);
+                size_t tb = s->sort_temp_bytes;
+                CK(cub::DeviceRadixSort::SortPairs(s->sort_temp, tb, s->sort_keys[0], s->sort_keys[1], s->sort_idx[0], s->sort_idx[1],
+                                                   (int)nb, 0, 31, stream));
+                k_sort_gather<<<blocks, kThreads, 0, stream>>>(s->q[cur], s->q[cur ^ 1], s->counts + b, s->sort_idx[1]);
+                cur ^= 1;
+                if (wt) wt->launches += 3;
+            }
+        }
+        PathQueue &qin = s->q[cur], &qout = s->q[cur ^ 1];
+        if (timing) CK(cudaEventRecord(s->events[ev++], stream));
         k_extend<<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->counts + b, s->counts + s->max_counts + b, wp);
         if (timing) CK(cudaEventRecord(s->events[ev++], stream));
         k_shade<<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, qout, s->counts + b, s->counts + b + 1, s->cx, s->cy, s->cz,
                                                  want_len ? s->path_len : nullptr, wp, (uint32_t)b);
         if (timing) CK(cudaEventRecord(s->events[ev++], stream));
+        cur ^= 1;
+        ++bounces_run;
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(s->counts_host, s->counts, sizeof(uint32_t) * (size_t)(max_depth + 1), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
-    for (int b = 0; b < max_depth; ++b) {
+    for (int b = 0; b < bounces_run; ++b) {
         *rays += s->counts_host[b];
         if (rays_per_bounce && b < RTGPU_MAX_BOUNCE_STATS) rays_per_bounce[b] += s->counts_host[b];
     }
     if (wt) {
-        wt->launches += 1 + 2 * (uint64_t)max_depth;
-        wt->launches_extend += (uint64_t)max_depth;
+        wt->launches += 1 + 2 * (uint64_t)bounces_run;
+        wt->launches_extend += (uint64_t)bounces_run;
         if (timing) {
             float ms = 0;
             CK(cudaEventElapsedTime(&ms, s->events[0], s->events[1]));
             wt->ms_other += ms;
-            for (int b = 0; b < max_depth; ++b) {
-                CK(cudaEventElapsedTime(&ms, s->events[1 + 2 * b], s->events[2 + 2 * b]));
+            for (int b = 0; b < bounces_run; ++b) {
+                if (b > 0) { /* sort between the previous shade and this extend */
+                    CK(cudaEventElapsedTime(&ms, s->events[1 + 3 * b], s->events[2 + 3 * b]));
+                    wt->ms_other += ms;
+                }
+                CK(cudaEventElapsedTime(&ms, s->events[2 + 3 * b], s->events[3 + 3 * b]));
                 wt->ms_extend += ms;
-                CK(cudaEventElapsedTime(&ms, s->events[2 + 2 * b], s->events[3 + 2 * b]));
+                CK(cudaEventElapsedTime(&ms, s->events[3 + 3 * b], s->events[4 + 3 * b]));
                 wt->ms_shade += ms;
             }
         }
@@ -584,6 +761,17 @@ rtgpu_status run_wave(rtgpu_scene *s, const WaveParams &wp, int max_depth, cudaS
 } // namespace
 
 extern "C" {
+
+#ifdef RT_DEBUG_COUNTERS
+int rtgpu_debug_counters(unsigned long long out[16], int reset) {
+    cudaMemcpyFromSymbol(out, g_dbg, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_dbg, z, sizeof z);
+    }
+    return 0;
+}
+#endif
 
 const char *rtgpu_last_error(void) { return g_err.c_str(); }
 
@@ -610,6 +798,16 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
     rtgpu_scene *s = new (std::nothrow) rtgpu_scene();
     if (!s) return RTGPU_ERR_OOM;
     s->device = cur;
+    {
+        std::lock_guard<std::mutex> lock(g_park_mutex);
+        if (cur >= 0 && cur < kMaxDevices && g_parked_valid[cur]) {
+            static_cast<WaveRes &>(*s) = g_parked[cur];
+            g_parked[cur] = WaveRes();
+            g_parked_valid[cur] = false;
+        }
+    }
+    if (const char *e = getenv("RTGPU_SORT_RAYS")) s->sort_mode = atoi(e);
+    if (const char *e = getenv("RTGPU_SORT_MIN")) s->sort_min = (uint32_t)atoll(e);
     memset(&s->d, 0, sizeof s->d);
 #define UP(field, src, n)                                                                                          \
     st = upload(s, src, (size_t)(n), &s->d.field);                                                                 \
@@ -640,11 +838,16 @@ rtgpu_status rtgpu_scene_destroy(rtgpu_scene *s) {
     if (!s) return RTGPU_OK;
     cudaSetDevice(s->device);
     for (void *p : s->allocs) cudaFree(p);
-    if (s->wave_mem) cudaFree(s->wave_mem);
-    if (s->counts) cudaFree(s->counts);
-    if (s->counts_host) cudaFreeHost(s->counts_host);
-    if (s->accum_dev) cudaFree(s->accum_dev);
-    for (cudaEvent_t e : s->events) cudaEventDestroy(e);
+    {
+        std::lock_guard<std::mutex> lock(g_park_mutex);
+        WaveRes &w = *s;
+        if (s->device >= 0 && s->device < kMaxDevices && !g_parked_valid[s->device] && w.cap > 0) {
+            g_parked[s->device] = w; /* keep the working memory for the next scene on this device */
+            g_parked_valid[s->device] = true;
+            w = WaveRes();
+        }
+    }
+    s->release();
     delete s;
     return RTGPU_OK;
 }
@@ -746,14 +949,23 @@ rtgpu_status rtgpu_trace_batch(rtgpu_scene *s, const rtgpu_ray *rays, int64_t n,
     if (ms_kernel) *ms_kernel = 0.;
     if (n == 0) return RTGPU_OK;
     CK(cudaSetDevice(s->device));
+    if (n > 0x7fffffff) {
+        g_err = "batch too large";
+        return RTGPU_ERR_INVALID_ARG;
+    }
     rtgpu_ray *d_rays = nullptr;
     uint64_t *d_keys = nullptr;
     rtgpu_hit *d_out = nullptr;
+    double *d_t = nullptr;
+    uint32_t *d_u32 = nullptr; /* op[n], rng_pos[n], fetch counter */
     rtgpu_status st = RTGPU_OK;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     auto body = [&]() -> rtgpu_status {
         CK(cudaMalloc(&d_rays, (size_t)n * sizeof(rtgpu_ray)));
         CK(cudaMalloc(&d_out, (size_t)n * sizeof(rtgpu_hit)));
+        CK(cudaMalloc(&d_t, (size_t)n * sizeof(double)));
+        CK(cudaMalloc(&d_u32, ((size_t)2 * n + 1) * sizeof(uint32_t)));
+        CK(cudaMemset(d_u32 + 2 * n, 0, sizeof(uint32_t)));
         CK(cudaMemcpy(d_rays, rays, (size_t)n * sizeof(rtgpu_ray), cudaMemcpyHostToDevice));
         if (keys) {
             CK(cudaMalloc(&d_keys, (size_t)n * sizeof(uint64_t)));
@@ -762,8 +974,9 @@ rtgpu_status rtgpu_trace_batch(rtgpu_scene *s, const rtgpu_ray *rays, int64_t n,
         CK(cudaEventCreate(&e0));
         CK(cudaEventCreate(&e1));
         CK(cudaEventRecord(e0, 0));
-        k_trace_batch<<<grid_blocks(), kThreads>>>(s->d, d_rays, d_keys, d_out, n);
+        k_trace_extend<<<grid_blocks(), kThreads>>>(s->d, d_rays, d_keys, d_t, d_u32, d_u32 + n, (uint32_t)n, d_u32 + 2 * n);
         CK(cudaEventRecord(e1, 0));
+        k_trace_record<<<grid_blocks(), kThreads>>>(s->d, d_rays, d_t, d_u32, d_u32 + n, d_out, (uint32_t)n);
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
         float ms = 0;
@@ -776,6 +989,8 @@ rtgpu_status rtgpu_trace_batch(rtgpu_scene *s, const rtgpu_ray *rays, int64_t n,
     if (d_rays) cudaFree(d_rays);
     if (d_keys) cudaFree(d_keys);
     if (d_out) cudaFree(d_out);
+    if (d_t) cudaFree(d_t);
+    if (d_u32) cudaFree(d_u32);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     return st;
