@@ -533,6 +533,8 @@ __device__ __forceinline__ void rect_record(HitRec &rec, V3 o, V3 d, double a0, 
     set_face_normal(rec, d, v3(AX == 0 ? 1. : 0., AX == 1 ? 1. : 0., AX == 2 ? 1. : 0.));
 }
 
+/* WANT_UV = false skips the sphere's acos/atan2 (only an ImageTexture reads u, v of a sphere) */
+template <bool WANT_UV>
 __device__ __noinline__ void make_record(const DScene &sc, const Ray &wr, double t, uint32_t opi, uint32_t face, HitRec &rec) {
     const rtgpu_op *op = sc.ops + opi;
     uint4 h = load_op_header(op);
@@ -564,7 +566,12 @@ __device__ __noinline__ void make_record(const DScene &sc, const Ray &wr, double
         }
         V3 at = o + d * t;
         V3 outward = (at - c) / p[3];
-        sphere_uv(outward, rec.u, rec.v);
+        if constexpr (WANT_UV) {
+            sphere_uv(outward, rec.u, rec.v);
+        } else {
+            rec.u = 0.;
+            rec.v = 0.;
+        }
         rec.p = at;
         set_face_normal(rec, d, outward);
         break;
@@ -632,6 +639,11 @@ __device__ __noinline__ void make_record(const DScene &sc, const Ray &wr, double
     }
 }
 
+/* f64 sin/cos expand to ~200 instructions each (plus the Payne-Hanek slow path); one out-of-line copy keeps
+ * k_shade small enough for the instruction cache (ncu: `no_instruction` was its top stall). */
+__device__ __noinline__ double rt_sin(double x) { return sin(x); }
+__device__ __noinline__ void rt_sincos(double x, double *s, double *c) { sincos(x, s, c); }
+
 /* ---- textures (texture/mod.rs, texture/perlin.rs) ------------------------------------------ */
 __device__ __forceinline__ int32_t floor_i32(double f) { /* `as i32`: saturating, NaN -> 0 */
     double fl = floor(f);
@@ -640,7 +652,7 @@ __device__ __forceinline__ int32_t floor_i32(double f) { /* `as i32`: saturating
     if (fl <= -2147483648.0) return (int32_t)0x80000000;
     return (int32_t)fl;
 }
-__device__ double perlin_noise(const rtgpu_perlin &t, V3 p) { /* perlin.rs:52-99 (double smoothing, Q9) */
+__device__ __noinline__ double perlin_noise(const rtgpu_perlin &t, V3 p) { /* perlin.rs:52-99 (double smoothing, Q9) */
     double u = p.x - floor(p.x), v = p.y - floor(p.y), w = p.z - floor(p.z);
     u = u * u * (3. - 2. * u);
     v = v * v * (3. - 2. * v);
@@ -673,38 +685,47 @@ __device__ double perlin_turb(const rtgpu_perlin &t, V3 p, int depth) { /* perli
     }
     return fabs(accum);
 }
-__device__ V3 texture_value(const DScene &sc, uint32_t id, double u, double v, V3 p) {
+/* TEXMASK: which texture kinds this instantiation can meet (bit k = rt_texture_kind k); the others are
+ * compiled out so that the per-material-class shade kernels stay small */
+#define RT_TEXMASK_SIMPLE 0x3 /* SolidColor, CheckerTexture over SolidColors */
+#define RT_TEXMASK_ALL 0xf
+template <int TEXMASK>
+__device__ __noinline__ V3 texture_value(const DScene &sc, uint32_t id, double u, double v, V3 p) {
     for (int depth = 0; depth < 16; ++depth) {
         const rtgpu_texture &t = sc.texs[id];
-        switch (t.kind) {
-        case 0: /* SolidColor, texture/mod.rs:25-29 */
+        uint32_t kind = t.kind;
+        if (kind == 0) /* SolidColor, texture/mod.rs:25-29 */
             return v3(t.p[0], t.p[1], t.p[2]);
-        case 1: { /* CheckerTexture, texture/mod.rs:52-59 */
-            double sines = sin(p.x * 10.) * sin(p.y * 10.) * sin(p.z * 10.);
+        if (kind == 1) { /* CheckerTexture, texture/mod.rs:52-59 */
+            double sines = rt_sin(p.x * 10.) * rt_sin(p.y * 10.) * rt_sin(p.z * 10.);
             id = (uint32_t)(sines < 0. ? t.a : t.b);
-            break;
+            continue;
         }
-        case 2: { /* NoiseTexture, texture/mod.rs:75-79 */
-            double s = 0.5 * (1. + sin(t.p[0] * p.z + 10. * perlin_turb(sc.perlins[t.a], p, 7)));
-            return v3(1. * s, 1. * s, 1. * s); /* Color(1,1,1) * 0.5 * (...) = ((1*0.5) * (...)) per channel */
+        if constexpr ((TEXMASK & 0x4) != 0) {
+            if (kind == 2) { /* NoiseTexture, texture/mod.rs:75-79 */
+                double s = 0.5 * (1. + rt_sin(t.p[0] * p.z + 10. * perlin_turb(sc.perlins[t.a], p, 7)));
+                return v3(1. * s, 1. * s, 1. * s); /* Color(1,1,1) * 0.5 * (...) */
+            }
         }
-        default: { /* ImageTexture, texture/mod.rs:110-138 */
-            if (t.a < 0) return v3(0., 1., 1.);
-            const rtgpu_image &im = sc.images[t.a];
-            if (u < 0.) u = 0.;
-            if (u > 1.) u = 1.; /* f64::clamp keeps NaN */
-            if (v < 0.) v = 0.;
-            if (v > 1.) v = 1.;
-            double fi = u * (double)im.width, fj = v * (double)im.height;
-            long long i = (fi > 0.) ? (fi >= 9.2e18 ? 0x7fffffffffffffffLL : (long long)fi) : 0; /* `as usize` */
-            long long j = (fj > 0.) ? (fj >= 9.2e18 ? 0x7fffffffffffffffLL : (long long)fj) : 0;
-            if (i >= im.width) i = im.width - 1;
-            if (j >= im.height) j = im.height - 1;
-            const double color_scale = 1. / 255.999;
-            const uint8_t *px = sc.texels + im.offset + 3 * (j * (long long)im.width + i);
-            return v3((double)__ldg(px) * color_scale, (double)__ldg(px + 1) * color_scale, (double)__ldg(px + 2) * color_scale);
+        if constexpr ((TEXMASK & 0x8) != 0) {
+            if (kind == 3) { /* ImageTexture, texture/mod.rs:110-138 */
+                if (t.a < 0) return v3(0., 1., 1.);
+                const rtgpu_image &im = sc.images[t.a];
+                if (u < 0.) u = 0.;
+                if (u > 1.) u = 1.; /* f64::clamp keeps NaN */
+                if (v < 0.) v = 0.;
+                if (v > 1.) v = 1.;
+                double fi = u * (double)im.width, fj = v * (double)im.height;
+                long long i = (fi > 0.) ? (fi >= 9.2e18 ? 0x7fffffffffffffffLL : (long long)fi) : 0; /* `as usize` */
+                long long j = (fj > 0.) ? (fj >= 9.2e18 ? 0x7fffffffffffffffLL : (long long)fj) : 0;
+                if (i >= im.width) i = im.width - 1;
+                if (j >= im.height) j = im.height - 1;
+                const double color_scale = 1. / 255.999;
+                const uint8_t *px = sc.texels + im.offset + 3 * (j * (long long)im.width + i);
+                return v3((double)__ldg(px) * color_scale, (double)__ldg(px + 1) * color_scale, (double)__ldg(px + 2) * color_scale);
+            }
         }
-        }
+        break;
     }
     return v3(0., 0., 0.);
 }
@@ -732,8 +753,10 @@ __device__ __forceinline__ V3 random_cosine_direction(rt_rng &rng) { /* pdf.rs:1
     double r2 = rng.gen();
     double z = sqrt(1. - r2);
     double phi = 2. * RT_PI * r1;
-    double x = cos(phi) * sqrt(r2);
-    double y = sin(phi) * sqrt(r2);
+    double sn, cs;
+    rt_sincos(phi, &sn, &cs);
+    double x = cs * sqrt(r2);
+    double y = sn * sqrt(r2);
     return v3(x, y, z);
 }
 __device__ __forceinline__ V3 random_to_sphere(rt_rng &rng, double radius, double dis_sqr) { /* vec.rs:108-117 */
@@ -741,8 +764,10 @@ __device__ __forceinline__ V3 random_to_sphere(rt_rng &rng, double radius, doubl
     double r2 = rng.gen();
     double z = 1. + r2 * (sqrt(1. - radius * radius / dis_sqr) - 1.);
     double phi = 2. * RT_PI * r1;
-    double x = cos(phi) * sqrt(1. - z * z);
-    double y = sin(phi) * sqrt(1. - z * z);
+    double sn, cs;
+    rt_sincos(phi, &sn, &cs);
+    double x = cs * sqrt(1. - z * z);
+    double y = sn * sqrt(1. - z * z);
     return v3(x, y, z);
 }
 struct Onb {
@@ -785,7 +810,7 @@ __device__ __forceinline__ double rect_pdf_value(const rtgpu_light &l, V3 o, V3 
     double cosv = fabs(dot(v, n) / length(v));
     return dis_sqr / (cosv * area);
 }
-__device__ double lights_pdf_value(const DScene &sc, V3 o, V3 v) {
+__device__ __noinline__ double lights_pdf_value(const DScene &sc, V3 o, V3 v) {
     double sum = 0.;
     for (uint32_t i = 0; i < sc.n_lights; ++i) {
         const rtgpu_light &l = sc.lights[i];
@@ -810,7 +835,7 @@ __device__ double lights_pdf_value(const DScene &sc, V3 o, V3 v) {
     }
     return sum / (double)sc.n_lights;
 }
-__device__ V3 lights_random(const DScene &sc, V3 o, rt_rng &rng) {
+__device__ __noinline__ V3 lights_random(const DScene &sc, V3 o, rt_rng &rng) {
     uint32_t target = rng.gen_index(sc.n_lights);
     const rtgpu_light &l = sc.lights[target];
     switch (l.kind) {

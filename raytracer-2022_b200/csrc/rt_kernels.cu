@@ -144,95 +144,134 @@ __global__ void __launch_bounds__(kThreads, RT_EXTEND_MIN_BLOCKS) k_extend(DScen
     extend_warp_loop(trav_of(sc), sc.n_ops, *count, fetch, io);
 }
 
-/* the body of ray_color (main.rs:233-278) for one segment; returns true when the path goes on */
-__device__ __forceinline__ bool shade_segment(const DScene &sc, const Ray &r, double t, uint32_t hop, rt_rng &rng,
-                                              V3 &beta, Ray &next, V3 &contrib) {
-    if (hop == RT_NO_HIT) { /* main.rs:275-277 */
-        contrib = beta * v3(sc.background[0], sc.background[1], sc.background[2]);
-        return false;
-    }
-    HitRec rec;
-    make_record(sc, r, t, hop & 0x1fffffffu, hop >> 29, rec);
-    const rtgpu_material &m = sc.mats[rec.mat];
-    switch (m.kind) {
-    case 3: { /* DiffuseLight: emitted, no scatter (material/mod.rs:173-181; main.rs:272-274) */
-        V3 e = rec.front ? texture_value(sc, m.tex, rec.u, rec.v, rec.p) : v3(0., 0., 0.);
-        contrib = beta * e;
-        return false;
-    }
-    case 1: { /* Metal, material/mod.rs:85-96: time reset to 0, no absorption test (Q6) */
-        V3 reflected = reflect(to_unit(r.d), rec.n);
-        next.o = rec.p;
-        next.d = reflected + random_in_unit_sphere(rng) * m.p[3];
-        next.tm = 0.;
-        beta = beta * v3(m.p[0], m.p[1], m.p[2]);
-        return true;
-    }
-    case 2: { /* Dielectric, material/mod.rs:120-147 */
-        double refraction_ratio = rec.front ? 1. / m.p[0] : m.p[0];
-        V3 unit_direction = to_unit(r.d);
-        double cos_theta = fmin(dot(-unit_direction, rec.n), 1.);
-        double sin_theta = sqrt(1. - cos_theta * cos_theta);
-        bool cannot_refract = refraction_ratio * sin_theta > 1.;
-        double random_double = rng.gen_range(0.0, 1.0);
-        V3 direction = (cannot_refract || reflectance(cos_theta, refraction_ratio) > random_double)
-                           ? reflect(unit_direction, rec.n)
-                           : refract(unit_direction, rec.n, refraction_ratio);
-        next.o = rec.p;
-        next.d = direction;
-        next.tm = r.tm;
-        return true; /* attenuation (1,1,1) */
-    }
-    case 4: { /* Isotropic, material/mod.rs:206-214 */
-        next.o = rec.p;
-        next.d = random_in_unit_sphere(rng);
-        next.tm = r.tm;
-        beta = beta * texture_value(sc, m.tex, rec.u, rec.v, rec.p);
-        return true;
-    }
-    default: { /* Lambertian + MixturePdf(HittablePdf(lights), CosPdf), main.rs:263-271 */
-        V3 attenuation = texture_value(sc, m.tex, rec.u, rec.v, rec.p);
-        Onb uvw = onb_from_w(rec.n); /* CosPdf::new(rec.normal), pdf.rs:35-39 */
-        V3 direction;
-        double pdf_val;
-        if (sc.n_lights == 0) {
-            /* Q12: empty `lights` -> the cosine pdf alone (decision shared with the oracle) */
-            direction = onb_local(uvw, random_cosine_direction(rng));
-            double c = dot(to_unit(direction), uvw.w);
-            pdf_val = c <= 0. ? 0. : c / RT_PI;
-        } else {
-            if (rng.gen_range(0.0, 1.0) < 0.5) /* MixturePdf::generate, pdf.rs:95-101 */
-                direction = lights_random(sc, rec.p, rng);
-            else
-                direction = onb_local(uvw, random_cosine_direction(rng));
-            double c = dot(to_unit(direction), uvw.w);
-            double cos_pdf = c <= 0. ? 0. : c / RT_PI;                            /* CosPdf::value, pdf.rs:46-53 */
-            pdf_val = 0.5 * lights_pdf_value(sc, rec.p, direction) + 0.5 * cos_pdf; /* pdf.rs:102-104 */
-        }
-        double cosine = dot(rec.n, to_unit(direction)); /* Lambertian::scattering_pdf, material/mod.rs:58-65 */
-        double spdf = cosine < 0. ? 0. : cosine / RT_PI;
-        next.o = rec.p;
-        next.d = direction;
-        next.tm = r.tm;
-        beta = beta * (attenuation * spdf / pdf_val); /* no pdf == 0 guard upstream either (Q10) */
-        return true;
-    }
-    }
-}
+/* ---- shading, split by material class ------------------------------------------------------------
+ * One monolithic shade kernel was 130 KB of SASS executed by warps whose lanes sat on five different
+ * materials: ncu showed 6.7 active lanes per instruction and `no_instruction` (instruction-cache miss)
+ * as the top stall.  Hits are therefore binned by material class first (k_classify: one warp-aggregated
+ * atomic per class), and each class runs its own small kernel over its own index list, so warps are
+ * uniform and every kernel fits the instruction cache.
+ *   class 0  path ends here: miss (background, main.rs:275-277) or DiffuseLight (main.rs:272-274)
+ *   class 1  Lambertian over SolidColor / Checker-of-solids      class 2  Lambertian over any texture
+ *   class 3  Metal            class 4  Dielectric                class 5  Isotropic (ConstantMedium) */
+constexpr int kClasses = 6;
 
-__global__ void __launch_bounds__(kThreads) k_shade(DScene sc, PathQueue qin, HitBuf hb, PathQueue qout, const uint32_t *count_in,
-                                                    uint32_t *count_out, double *cx, double *cy, double *cz, uint32_t *path_len,
-                                                    WaveParams wp, uint32_t bounce) {
+__global__ void __launch_bounds__(256) k_classify(DScene sc, const uint8_t *mat_class, HitBuf hb, const uint32_t *count_in,
+                                                  uint32_t *class_count, uint32_t *class_idx, uint32_t cap) {
     uint32_t n = *count_in;
     uint32_t stride = gridDim.x * blockDim.x;
     uint32_t lane = threadIdx.x & 31u;
     for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < n; i0 += stride) {
         uint32_t i = i0 + lane;
+        uint32_t cls = 0xffu;
+        if (i < n) {
+            uint32_t hop = hb.op[i];
+            cls = 0;
+            if (hop != RT_NO_HIT) cls = mat_class[load_op_header(sc.ops + (hop & 0x1fffffffu)).z];
+        }
+        uint32_t peers = __match_any_sync(0xffffffffu, cls);
+        if (cls != 0xffu) {
+            int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(class_count + cls, (uint32_t)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            class_idx[(size_t)cls * cap + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = i;
+        }
+    }
+}
+
+/* the body of ray_color (main.rs:233-278) for one segment of a path whose hit is of class CLS;
+ * returns true when the path goes on */
+template <int CLS>
+__device__ __forceinline__ bool shade_segment(const DScene &sc, const Ray &r, double t, uint32_t hop, rt_rng &rng, V3 &beta,
+                                              Ray &next, V3 &contrib) {
+    if constexpr (CLS == 0) {
+        if (hop == RT_NO_HIT) { /* main.rs:275-277 */
+            contrib = beta * v3(sc.background[0], sc.background[1], sc.background[2]);
+            return false;
+        }
+        /* DiffuseLight: emitted, no scatter (material/mod.rs:173-181; main.rs:272-274) */
+        HitRec rec;
+        make_record<true>(sc, r, t, hop & 0x1fffffffu, hop >> 29, rec);
+        const rtgpu_material &m = sc.mats[rec.mat];
+        V3 e = rec.front ? texture_value<RT_TEXMASK_ALL>(sc, m.tex, rec.u, rec.v, rec.p) : v3(0., 0., 0.);
+        contrib = beta * e;
+        return false;
+    } else {
+        HitRec rec;
+        make_record<CLS == 2 || CLS == 5>(sc, r, t, hop & 0x1fffffffu, hop >> 29, rec);
+        const rtgpu_material &m = sc.mats[rec.mat];
+        if constexpr (CLS == 3) { /* Metal, material/mod.rs:85-96: time reset to 0, no absorption test (Q6) */
+            V3 reflected = reflect(to_unit(r.d), rec.n);
+            next.o = rec.p;
+            next.d = reflected + random_in_unit_sphere(rng) * m.p[3];
+            next.tm = 0.;
+            beta = beta * v3(m.p[0], m.p[1], m.p[2]);
+            return true;
+        } else if constexpr (CLS == 4) { /* Dielectric, material/mod.rs:120-147 */
+            double refraction_ratio = rec.front ? 1. / m.p[0] : m.p[0];
+            V3 unit_direction = to_unit(r.d);
+            double cos_theta = fmin(dot(-unit_direction, rec.n), 1.);
+            double sin_theta = sqrt(1. - cos_theta * cos_theta);
+            bool cannot_refract = refraction_ratio * sin_theta > 1.;
+            double random_double = rng.gen_range(0.0, 1.0);
+            V3 direction = (cannot_refract || reflectance(cos_theta, refraction_ratio) > random_double)
+                               ? reflect(unit_direction, rec.n)
+                               : refract(unit_direction, rec.n, refraction_ratio);
+            next.o = rec.p;
+            next.d = direction;
+            next.tm = r.tm;
+            return true; /* attenuation (1,1,1) */
+        } else if constexpr (CLS == 5) { /* Isotropic, material/mod.rs:206-214 */
+            next.o = rec.p;
+            next.d = random_in_unit_sphere(rng);
+            next.tm = r.tm;
+            beta = beta * texture_value<RT_TEXMASK_ALL>(sc, m.tex, rec.u, rec.v, rec.p);
+            return true;
+        } else { /* Lambertian + MixturePdf(HittablePdf(lights), CosPdf), main.rs:263-271 */
+            V3 attenuation = texture_value<(CLS == 1 ? RT_TEXMASK_SIMPLE : RT_TEXMASK_ALL)>(sc, m.tex, rec.u, rec.v, rec.p);
+            Onb uvw = onb_from_w(rec.n); /* CosPdf::new(rec.normal), pdf.rs:35-39 */
+            V3 direction;
+            double pdf_val;
+            if (sc.n_lights == 0) {
+                /* Q12: empty `lights` -> the cosine pdf alone (decision shared with the oracle) */
+                direction = onb_local(uvw, random_cosine_direction(rng));
+                double c = dot(to_unit(direction), uvw.w);
+                pdf_val = c <= 0. ? 0. : c / RT_PI;
+            } else {
+                if (rng.gen_range(0.0, 1.0) < 0.5) /* MixturePdf::generate, pdf.rs:95-101 */
+                    direction = lights_random(sc, rec.p, rng);
+                else
+                    direction = onb_local(uvw, random_cosine_direction(rng));
+                double c = dot(to_unit(direction), uvw.w);
+                double cos_pdf = c <= 0. ? 0. : c / RT_PI;                            /* CosPdf::value, pdf.rs:46-53 */
+                pdf_val = 0.5 * lights_pdf_value(sc, rec.p, direction) + 0.5 * cos_pdf; /* pdf.rs:102-104 */
+            }
+            double cosine = dot(rec.n, to_unit(direction)); /* Lambertian::scattering_pdf, material/mod.rs:58-65 */
+            double spdf = cosine < 0. ? 0. : cosine / RT_PI;
+            next.o = rec.p;
+            next.d = direction;
+            next.tm = r.tm;
+            beta = beta * (attenuation * spdf / pdf_val); /* no pdf == 0 guard upstream either (Q10) */
+            return true;
+        }
+    }
+}
+
+template <int CLS>
+__global__ void __launch_bounds__(kThreads) k_shade(DScene sc, PathQueue qin, HitBuf hb, PathQueue qout, const uint32_t *class_count,
+                                                    const uint32_t *class_idx, uint32_t *count_out, double *cx, double *cy, double *cz,
+                                                    uint32_t *path_len, WaveParams wp, uint32_t bounce) {
+    uint32_t n = class_count[CLS];
+    uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t j0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; j0 < n; j0 += stride) {
+        uint32_t j = j0 + lane;
         bool alive = false;
         Ray next;
         V3 beta;
         uint32_t pid = 0, pos = 0;
-        if (i < n) {
+        if (j < n) {
+            uint32_t i = class_idx[j];
             Ray r;
             r.o = v3(qin.ox[i], qin.oy[i], qin.oz[i]);
             r.d = v3(qin.dx[i], qin.dy[i], qin.dz[i]);
@@ -242,7 +281,7 @@ __global__ void __launch_bounds__(kThreads) k_shade(DScene sc, PathQueue qin, Hi
             rt_rng rng;
             path_rng(rng, wp, pid, qin.rng[i]);
             V3 contrib;
-            alive = shade_segment(sc, r, hb.t[i], hb.op[i], rng, beta, next, contrib);
+            alive = shade_segment<CLS>(sc, r, hb.t[i], hb.op[i], rng, beta, next, contrib);
             pos = rng.pos;
             if (!alive) {
                 cx[pid] = contrib.x;
@@ -251,22 +290,24 @@ __global__ void __launch_bounds__(kThreads) k_shade(DScene sc, PathQueue qin, Hi
                 if (path_len) path_len[pid] = bounce + 1;
             }
         }
-        /* compaction: one atomic per warp, survivors packed in lane order */
-        __syncwarp();
-        uint32_t mask = __ballot_sync(0xffffffffu, alive);
-        if (mask) {
-            uint32_t base = 0;
-            int leader = __ffs(mask) - 1;
-            if ((int)lane == leader) base = atomicAdd(count_out, (uint32_t)__popc(mask));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (alive) {
-                uint32_t j = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
-                qout.ox[j] = next.o.x; qout.oy[j] = next.o.y; qout.oz[j] = next.o.z;
-                qout.dx[j] = next.d.x; qout.dy[j] = next.d.y; qout.dz[j] = next.d.z;
-                qout.tm[j] = next.tm;
-                qout.bx[j] = beta.x; qout.by[j] = beta.y; qout.bz[j] = beta.z;
-                qout.pid[j] = pid;
-                qout.rng[j] = pos;
+        if constexpr (CLS != 0) {
+            /* compaction: one atomic per warp, survivors packed in lane order */
+            __syncwarp();
+            uint32_t mask = __ballot_sync(0xffffffffu, alive);
+            if (mask) {
+                uint32_t base = 0;
+                int leader = __ffs(mask) - 1;
+                if ((int)lane == leader) base = atomicAdd(count_out, (uint32_t)__popc(mask));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (alive) {
+                    uint32_t k = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+                    qout.ox[k] = next.o.x; qout.oy[k] = next.o.y; qout.oz[k] = next.o.z;
+                    qout.dx[k] = next.d.x; qout.dy[k] = next.d.y; qout.dz[k] = next.d.z;
+                    qout.tm[k] = next.tm;
+                    qout.bx[k] = beta.x; qout.by[k] = beta.y; qout.bz[k] = beta.z;
+                    qout.pid[k] = pid;
+                    qout.rng[k] = pos;
+                }
             }
         }
     }
@@ -439,7 +480,7 @@ __global__ void __launch_bounds__(kThreads) k_trace_record(DScene sc, const rtgp
         h.rng_pos = rng_pos[i];
         if (op[i] != RT_NO_HIT) {
             HitRec rec;
-            make_record(sc, r, t[i], op[i] & 0x1fffffffu, op[i] >> 29, rec);
+            make_record<true>(sc, r, t[i], op[i] & 0x1fffffffu, op[i] >> 29, rec);
             h.hit = 1;
             h.t = rec.t;
             h.p[0] = rec.p.x; h.p[1] = rec.p.y; h.p[2] = rec.p.z;
@@ -503,6 +544,8 @@ struct WaveRes {
     HitBuf hb;
     double *cx = nullptr, *cy = nullptr, *cz = nullptr;
     uint32_t *path_len = nullptr;
+    uint32_t *class_idx = nullptr;   /* kClasses lists of queue indices, `cap` entries each */
+    uint32_t *class_count = nullptr; /* device: [bounce][8] */
     uint32_t *counts = nullptr;      /* device: queue length per bounce, then the fetch counters */
     uint32_t *counts_host = nullptr; /* pinned */
     int max_counts = 0;
@@ -517,6 +560,7 @@ struct WaveRes {
     void release() {
         if (wave_mem) cudaFree(wave_mem);
         if (counts) cudaFree(counts);
+        if (class_count) cudaFree(class_count);
         if (counts_host) cudaFreeHost(counts_host);
         if (accum_dev) cudaFree(accum_dev);
         if (sort_temp) cudaFree(sort_temp);
@@ -529,6 +573,8 @@ struct rtgpu_scene : WaveRes {
     int device = 0;
     DScene d;
     std::vector<void *> allocs;
+    const uint8_t *mat_class = nullptr; /* device: shade class per material */
+    bool class_present[8] = {true, false, false, false, false, false, false, false};
     int sort_mode = 0; /* RTGPU_SORT_RAYS=1: reorder rays between bounces */
     uint32_t sort_min = 1u << 16;
 };
@@ -625,12 +671,15 @@ int grid_blocks() { return kSMs * kBlocksPerSM; }
 rtgpu_status ensure_wave(rtgpu_scene *s, size_t n_paths, int max_depth) {
     if (max_depth + 2 > s->max_counts) {
         if (s->counts) cudaFree(s->counts);
+        if (s->class_count) cudaFree(s->class_count);
         if (s->counts_host) cudaFreeHost(s->counts_host);
         s->counts = nullptr;
+        s->class_count = nullptr;
         s->counts_host = nullptr;
         s->max_counts = max_depth + 2;
         CK(cudaMalloc(&s->counts, 2 * sizeof(uint32_t) * (size_t)s->max_counts)); /* queue lengths, then fetch counters */
         CK(cudaMallocHost(&s->counts_host, sizeof(uint32_t) * (size_t)s->max_counts));
+        CK(cudaMalloc(&s->class_count, 8 * sizeof(uint32_t) * (size_t)s->max_counts));
     }
     if (n_paths <= s->cap) return RTGPU_OK;
     if (s->wave_mem) cudaFree(s->wave_mem);
@@ -638,7 +687,7 @@ rtgpu_status ensure_wave(rtgpu_scene *s, size_t n_paths, int max_depth) {
     s->cap = 0;
     size_t n = (n_paths + 255) & ~(size_t)255;
     /* per path: 2 queues x (10 doubles + 2 u32) + hit (double + u32) + contrib (3 doubles) + path_len */
-    size_t bytes = n * (2 * (10 * 8 + 2 * 4) + 8 + 4 + 3 * 8 + 4 + 4 * 4) + 256;
+    size_t bytes = n * (2 * (10 * 8 + 2 * 4) + 8 + 4 + 3 * 8 + 4 + 4 * 4 + kClasses * 4) + 256;
     CK(cudaMalloc(&s->wave_mem, bytes));
     char *p = static_cast<char *>(s->wave_mem);
     auto take_d = [&](double *&dst) { dst = reinterpret_cast<double *>(p); p += n * 8; };
@@ -653,6 +702,8 @@ rtgpu_status ensure_wave(rtgpu_scene *s, size_t n_paths, int max_depth) {
     for (int k = 0; k < 2; ++k) { take_u(s->q[k].pid); take_u(s->q[k].rng); }
     take_u(s->hb.op);
     take_u(s->path_len);
+    s->class_idx = reinterpret_cast<uint32_t *>(p);
+    p += n * 4 * kClasses;
     take_u(s->sort_keys[0]); take_u(s->sort_keys[1]); take_u(s->sort_idx[0]); take_u(s->sort_idx[1]);
     s->sort_bounds = reinterpret_cast<double *>(p + ((8 - ((size_t)p & 7)) & 7));
     {
@@ -682,6 +733,7 @@ rtgpu_status run_wave(rtgpu_scene *s, const WaveParams &wp, int max_depth, cudaS
     if (st != RTGPU_OK) return st;
     size_t n = wp.n_paths;
     CK(cudaMemsetAsync(s->counts, 0, 2 * sizeof(uint32_t) * (size_t)s->max_counts, stream));
+    CK(cudaMemsetAsync(s->class_count, 0, 8 * sizeof(uint32_t) * (size_t)s->max_counts, stream));
     CK(cudaMemcpyAsync(s->counts, &wp.n_paths, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
     CK(cudaMemsetAsync(s->cx, 0, n * 8, stream));
     CK(cudaMemsetAsync(s->cy, 0, n * 8, stream));
@@ -701,6 +753,12 @@ rtgpu_status run_wave(rtgpu_scene *s, const WaveParams &wp, int max_depth, cudaS
     int cur = 0; /* queue that holds the rays of the current bounce */
     int bounces_run = 0;
     for (int b = 0; b < max_depth; ++b) {
+        if (!s->sort_mode && b > 0 && (b % 8) == 0) {
+            /* every 8 bounces: is anything still alive? (one 4-byte readback) */
+            CK(cudaMemcpyAsync(s->counts_host + b, s->counts + b, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            if (s->counts_host[b] == 0) break;
+        }
         if (s->sort_mode && b >= 1) {
             /* the queue length is needed on the host to size the sort (one small readback per bounce) */
             CK(cudaMemcpyAsync(s->counts_host + b, s->counts + b, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
@@ -723,8 +781,23 @@ rtgpu_status run_wave(rtgpu_scene *s, const WaveParams &wp, int max_depth, cudaS
         if (timing) CK(cudaEventRecord(s->events[ev++], stream));
         k_extend<<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->counts + b, s->counts + s->max_counts + b, wp);
         if (timing) CK(cudaEventRecord(s->events[ev++], stream));
-        k_shade<<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, qout, s->counts + b, s->counts + b + 1, s->cx, s->cy, s->cz,
-                                                 want_len ? s->path_len : nullptr, wp, (uint32_t)b);
+        {
+            uint32_t *cc = s->class_count + 8 * b;
+            uint32_t *pl = want_len ? s->path_len : nullptr;
+            uint32_t cap = (uint32_t)s->cap;
+            k_classify<<<blocks, 256, 0, stream>>>(s->d, s->mat_class, s->hb, s->counts + b, cc, s->class_idx, cap);
+#define RT_SHADE(C) k_shade<C><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, qout, cc, s->class_idx + (size_t)C * cap, s->counts + b + 1, \
+                                                                s->cx, s->cy, s->cz, pl, wp, (uint32_t)b)
+            int n_launched = 0;
+            RT_SHADE(0);
+            if (s->class_present[1]) { RT_SHADE(1); ++n_launched; }
+            if (s->class_present[2]) { RT_SHADE(2); ++n_launched; }
+            if (s->class_present[3]) { RT_SHADE(3); ++n_launched; }
+            if (s->class_present[4]) { RT_SHADE(4); ++n_launched; }
+            if (s->class_present[5]) { RT_SHADE(5); ++n_launched; }
+            if (wt) wt->launches += 2 + (uint64_t)n_launched; /* classify + class 0 + the others */
+#undef RT_SHADE
+        }
         if (timing) CK(cudaEventRecord(s->events[ev++], stream));
         cur ^= 1;
         ++bounces_run;
@@ -737,7 +810,7 @@ rtgpu_status run_wave(rtgpu_scene *s, const WaveParams &wp, int max_depth, cudaS
         if (rays_per_bounce && b < RTGPU_MAX_BOUNCE_STATS) rays_per_bounce[b] += s->counts_host[b];
     }
     if (wt) {
-        wt->launches += 1 + 2 * (uint64_t)bounces_run;
+        wt->launches += 1 + (uint64_t)bounces_run; /* raygen + extends; shade launches counted in the loop */
         wt->launches_extend += (uint64_t)bounces_run;
         if (timing) {
             float ms = 0;
@@ -825,6 +898,31 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
     UP(images, desc->images, desc->n_images)
     UP(texels, desc->texels, desc->n_texel_bytes)
     UP(lights, desc->lights, desc->n_lights)
+    {
+        /* shade class per material (see k_classify) */
+        std::vector<uint8_t> mc(desc->n_materials ? desc->n_materials : 1, 2);
+        auto simple_tex = [&](uint32_t t) {
+            const rtgpu_texture &x = desc->textures[t];
+            if (x.kind == 0) return true;
+            return x.kind == 1 && desc->textures[x.a].kind == 0 && desc->textures[x.b].kind == 0;
+        };
+        for (uint32_t i = 0; i < desc->n_materials; ++i) {
+            const rtgpu_material &m = desc->materials[i];
+            switch (m.kind) {
+            case 0: mc[i] = simple_tex(m.tex) ? 1 : 2; break;
+            case 1: mc[i] = 3; break;
+            case 2: mc[i] = 4; break;
+            case 3: mc[i] = 0; break;
+            default: mc[i] = 5; break;
+            }
+            s->class_present[mc[i]] = true;
+        }
+        st = upload(s, mc.data(), mc.size(), &s->mat_class);
+        if (st != RTGPU_OK) {
+            rtgpu_scene_destroy(s);
+            return st;
+        }
+    }
 #undef UP
     s->d.n_ops = desc->n_ops;
     s->d.n_lights = desc->n_lights;
