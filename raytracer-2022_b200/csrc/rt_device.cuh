@@ -79,6 +79,13 @@ __device__ __forceinline__ void load_slot8(const rtgpu_op *op, double d[8]) { /*
     d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y; d[4] = c.x; d[5] = c.y; d[6] = e.x; d[7] = e.y;
 }
 
+template <bool SMEM>
+__device__ __forceinline__ uint4 op_header(const struct TravScene &sc, uint32_t i);
+template <bool SMEM>
+__device__ __forceinline__ void op_payload(const struct TravScene &sc, uint32_t i, double d[6]);
+template <bool SMEM>
+__device__ __forceinline__ void op_slot8(const struct TravScene &sc, uint32_t i, double d[8]);
+
 /* ---- wrappers: ray into object space (hittable/mod.rs:166,240-248,322) -------------------- */
 __device__ __forceinline__ void xform_ray(const rtgpu_xform &xf, V3 &o, V3 &d) {
     switch (xf.kind) {
@@ -105,8 +112,22 @@ struct TravScene {
     const rtgpu_op *ops;
     const rtgpu_xform *xforms;
     const uint32_t *chain;
+    uint32_t sm_ops; /* shared-memory address of a staged copy of `ops` (SMEM variants), else 0 */
 };
-__device__ __forceinline__ TravScene trav_of(const DScene &sc) { return TravScene{sc.ops, sc.xforms, sc.chain}; }
+__device__ __forceinline__ TravScene trav_of(const DScene &sc, uint32_t sm_ops = 0) {
+    return TravScene{sc.ops, sc.xforms, sc.chain, sm_ops};
+}
+/* op fetch: from HBM/L2/L1 through the read-only path, or from the copy staged in shared memory */
+__device__ __forceinline__ uint4 lds_u128(uint32_t a) {
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t a) {
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ rtgpu_xform load_xform(const TravScene &sc, uint32_t chain_idx) {
     const rtgpu_xform *x = sc.xforms + __ldg(sc.chain + chain_idx);
     const double2 *p = reinterpret_cast<const double2 *>(x);
@@ -117,6 +138,32 @@ __device__ __forceinline__ rtgpu_xform load_xform(const TravScene &sc, uint32_t 
     r.gid = hdr.y;
     r.p[0] = a.y; r.p[1] = b.x; r.p[2] = b.y;
     return r;
+}
+
+template <bool SMEM>
+__device__ __forceinline__ uint4 op_header(const TravScene &sc, uint32_t i) {
+    if constexpr (SMEM) return lds_u128(sc.sm_ops + i * 64u);
+    else return load_op_header(sc.ops + i);
+}
+template <bool SMEM>
+__device__ __forceinline__ void op_payload(const TravScene &sc, uint32_t i, double d[6]) {
+    if constexpr (SMEM) {
+        uint32_t a = sc.sm_ops + i * 64u + 16u;
+        double2 x = lds_f64x2(a), y = lds_f64x2(a + 16u), z = lds_f64x2(a + 32u);
+        d[0] = x.x; d[1] = x.y; d[2] = y.x; d[3] = y.y; d[4] = z.x; d[5] = z.y;
+    } else {
+        load_op_payload(sc.ops + i, d);
+    }
+}
+template <bool SMEM>
+__device__ __forceinline__ void op_slot8(const TravScene &sc, uint32_t i, double d[8]) {
+    if constexpr (SMEM) {
+        uint32_t a = sc.sm_ops + i * 64u;
+        double2 x = lds_f64x2(a), y = lds_f64x2(a + 16u), z = lds_f64x2(a + 32u), w = lds_f64x2(a + 48u);
+        d[0] = x.x; d[1] = x.y; d[2] = y.x; d[3] = y.y; d[4] = z.x; d[5] = z.y; d[6] = w.x; d[7] = w.y;
+    } else {
+        load_slot8(sc.ops + i, d);
+    }
 }
 
 /* ---- primitive tests: return true and shrink `best` on a hit ------------------------------- */
@@ -182,18 +229,21 @@ __device__ __forceinline__ bool hit_triangle(V3 o, V3 d, V3 a, V3 b, V3 c, V3 n,
  * is equivalent to the per-axis early exits (both bounds are monotone).  The comparisons keep
  * upstream's polarity, so NaN (0 * inf) leaves a bound unchanged. */
 struct RaySigns {
-    bool x, y, z; /* inv.* < 0 */
+    uint32_t m; /* bit 0/1/2: inv.x/y/z < 0 */
+    __device__ __forceinline__ bool x() const { return m & 1u; }
+    __device__ __forceinline__ bool y() const { return m & 2u; }
+    __device__ __forceinline__ bool z() const { return m & 4u; }
 };
 __device__ __forceinline__ bool hit_aabb(V3 o, V3 inv, RaySigns sg, const double b[6], double tmin, double tmax) {
-    double t0 = ((sg.x ? b[3] : b[0]) - o.x) * inv.x, t1 = ((sg.x ? b[0] : b[3]) - o.x) * inv.x;
+    double t0 = ((sg.x() ? b[3] : b[0]) - o.x) * inv.x, t1 = ((sg.x() ? b[0] : b[3]) - o.x) * inv.x;
     tmin = t0 > tmin ? t0 : tmin;
     tmax = t1 < tmax ? t1 : tmax;
-    t0 = ((sg.y ? b[4] : b[1]) - o.y) * inv.y;
-    t1 = ((sg.y ? b[1] : b[4]) - o.y) * inv.y;
+    t0 = ((sg.y() ? b[4] : b[1]) - o.y) * inv.y;
+    t1 = ((sg.y() ? b[1] : b[4]) - o.y) * inv.y;
     tmin = t0 > tmin ? t0 : tmin;
     tmax = t1 < tmax ? t1 : tmax;
-    t0 = ((sg.z ? b[5] : b[2]) - o.z) * inv.z;
-    t1 = ((sg.z ? b[2] : b[5]) - o.z) * inv.z;
+    t0 = ((sg.z() ? b[5] : b[2]) - o.z) * inv.z;
+    t1 = ((sg.z() ? b[2] : b[5]) - o.z) * inv.z;
     tmin = t0 > tmin ? t0 : tmin;
     tmax = t1 < tmax ? t1 : tmax;
     return !(tmax <= tmin);
@@ -213,17 +263,15 @@ struct Closest {
  * `rng` draws the medium's free path (constantmedium.rs:60) in visiting order. */
 struct RayState {
     V3 o, d, inv;
-    double a; /* |d|^2 */
     RaySigns sg;
+    __device__ __forceinline__ double a() const { return length_sqr(d); } /* |d|^2, recomputed where a sphere needs it */
 };
 __device__ __forceinline__ void ray_state_derive(RayState &r) {
     r.inv = v3(1. / r.d.x, 1. / r.d.y, 1. / r.d.z);
-    r.a = length_sqr(r.d);
-    r.sg.x = r.inv.x < 0.;
-    r.sg.y = r.inv.y < 0.;
-    r.sg.z = r.inv.z < 0.;
+    r.sg.m = (r.inv.x < 0. ? 1u : 0u) | (r.inv.y < 0. ? 2u : 0u) | (r.inv.z < 0. ? 4u : 0u);
 }
 
+template <bool SMEM>
 __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm,
                                                      double tmin, double tmax);
 
@@ -242,6 +290,7 @@ struct SavedRays {
  * 128-bit loads issued together) is fetched as soon as the index is known; exec_*() consume it.
  * One call of exec handles one op, so a warp can run "all lanes that sit on a NODE" together,
  * then "all lanes that sit on a sphere", ... (see extend_warp_loop). */
+template <bool SMEM>
 struct Traversal {
     RayState r;
     double tm, tmin;
@@ -253,12 +302,16 @@ struct Traversal {
     /* the PUSH/POP stack lives OUTSIDE this struct (SavedRays): it is indexed dynamically, and an
      * aggregate with a dynamically indexed member is kept in local memory as a whole */
 
+    /* global variant: header + payload prefetched together (hides the L1/L2 latency behind the vote);
+     * shared variant: header now, payload at use (short live range, 12 registers fewer in the loop) */
     __device__ __forceinline__ void fetch_op(const TravScene sc) {
         if (i < end) {
-            const rtgpu_op *op = sc.ops + i;
-            h = load_op_header(op);
-            load_op_payload(op, p);
+            h = op_header<SMEM>(sc, i);
+            if constexpr (!SMEM) op_payload<false>(sc, i, p);
         }
+    }
+    __device__ __forceinline__ void need_payload(const TravScene sc) {
+        if constexpr (SMEM) op_payload<true>(sc, i, p);
     }
     __device__ __forceinline__ void start(const TravScene sc, uint32_t begin, uint32_t end_, V3 o, V3 d, double tm_, double tmin_,
                                           double tmax) {
@@ -279,30 +332,34 @@ struct Traversal {
     __device__ __forceinline__ uint32_t phase() const { return phase_of_kind(h.x & 0xffu); }
 
     __device__ __forceinline__ void exec_node(const TravScene sc) {
+        need_payload(sc);
         i = hit_aabb(r.o, r.inv, r.sg, p, tmin, best.t) ? i + 1 : h.y;
         fetch_op(sc);
     }
     __device__ __forceinline__ void exec_sphere(const TravScene sc) {
+        need_payload(sc);
         V3 c = v3(p[0], p[1], p[2]);
         uint32_t width = 1;
         if ((h.x & 0xffu) == RTGPU_OP_MSPHERE) { /* MovingSphere::center, sphere.rs:124-127 */
             double q[8];
-            load_slot8(sc.ops + i + 1, q);
+            op_slot8<SMEM>(sc, i + 1, q);
             c = c + (v3(q[0], q[1], q[2]) - c) * ((tm - p[4]) / (p[5] - p[4]));
             width = 2;
         }
-        if (hit_sphere(r.o, r.d, r.a, c, p[3], tmin, best.t)) best.op = i;
+        if (hit_sphere(r.o, r.d, r.a(), c, p[3], tmin, best.t)) best.op = i;
         i += width;
         fetch_op(sc);
     }
     __device__ __forceinline__ void exec_box(const TravScene sc) {
+        need_payload(sc);
         if (hit_box(r.o, r.d, p, tmin, best.t, best.face)) best.op = i;
         i += 1;
         fetch_op(sc);
     }
     __device__ __forceinline__ void exec_tri(const TravScene sc) {
+        need_payload(sc);
         double q[8];
-        load_slot8(sc.ops + i + 1, q);
+        op_slot8<SMEM>(sc, i + 1, q);
         if (hit_triangle(r.o, r.d, v3(p[0], p[1], p[2]), v3(p[3], p[4], p[5]), v3(q[0], q[1], q[2]), v3(q[3], q[4], q[5]), tmin,
                          best.t))
             best.op = i;
@@ -312,6 +369,7 @@ struct Traversal {
     /* rects, ConstantMedium, PUSH, POP.  DRAW() = next uniform of the ray's stream */
     template <bool MAIN, typename DRAW>
     __device__ __forceinline__ void exec_misc(const TravScene sc, SavedRays &stk, DRAW &&draw) {
+        need_payload(sc);
         switch (h.x & 0xffu) {
         case RTGPU_OP_RECT_XY:
             if (hit_rect<2>(r.o, r.d, p[0], p[1], p[2], p[3], p[4], tmin, best.t)) best.op = i;
@@ -330,19 +388,19 @@ struct Traversal {
                 double t1 = CUDART_INF, t2 = CUDART_INF;
                 bool h1, h2 = false;
                 bool single_sphere = h.y == i + 2;
-                if (single_sphere) single_sphere = (load_op_header(sc.ops + i + 1).x & 0xffu) == RTGPU_OP_SPHERE;
+                if (single_sphere) single_sphere = (op_header<SMEM>(sc, i + 1).x & 0xffu) == RTGPU_OP_SPHERE;
                 if (single_sphere) { /* boundary = one Sphere (both media of final_scene) */
                     double bp[6];
-                    load_op_payload(sc.ops + i + 1, bp);
+                    op_payload<SMEM>(sc, i + 1, bp);
                     V3 c = v3(bp[0], bp[1], bp[2]);
-                    h1 = hit_sphere(r.o, r.d, r.a, c, bp[3], -CUDART_INF, t1);
-                    if (h1) h2 = hit_sphere(r.o, r.d, r.a, c, bp[3], t1 + 0.0001, t2);
+                    h1 = hit_sphere(r.o, r.d, r.a(), c, bp[3], -CUDART_INF, t1);
+                    if (h1) h2 = hit_sphere(r.o, r.d, r.a(), c, bp[3], t1 + 0.0001, t2);
                 } else {
-                    Closest r1 = closest_hit_boundary(sc, i + 1, h.y, r.o, r.d, tm, -CUDART_INF, CUDART_INF);
+                    Closest r1 = closest_hit_boundary<SMEM>(sc, i + 1, h.y, r.o, r.d, tm, -CUDART_INF, CUDART_INF);
                     h1 = r1.op != RT_NO_HIT;
                     t1 = r1.t;
                     if (h1) {
-                        Closest r2 = closest_hit_boundary(sc, i + 1, h.y, r.o, r.d, tm, t1 + 0.0001, CUDART_INF);
+                        Closest r2 = closest_hit_boundary<SMEM>(sc, i + 1, h.y, r.o, r.d, tm, t1 + 0.0001, CUDART_INF);
                         h2 = r2.op != RT_NO_HIT;
                         t2 = r2.t;
                     }
@@ -352,7 +410,7 @@ struct Traversal {
                     t2 = fmin(t2, best.t);
                     if (!(t1 >= t2)) {
                         t1 = fmax(t1, 0.);
-                        double ray_length = sqrt(r.a);
+                        double ray_length = sqrt(r.a());
                         double distance_inside_boundary = (t2 - t1) * ray_length;
                         double rnd = draw();
                         double hit_distance = p[0] * log(rnd); /* neg_inv_density * rnd.log(E) */
@@ -401,12 +459,13 @@ struct Traversal {
 };
 
 /* boundary walk of a medium whose boundary is not a single sphere: rare, kept out of line */
+template <bool SMEM>
 __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm,
                                                      double tmin, double tmax) {
-    Traversal tr;
+    Traversal<SMEM> tr;
     SavedRays stk;
     tr.start(sc, begin, end, o, d, tm, tmin, tmax);
-    while (!tr.done()) tr.step<false>(sc, stk, []() { return 0.; });
+    while (!tr.done()) tr.template step<false>(sc, stk, []() { return 0.; });
     return tr.best;
 }
 
@@ -429,10 +488,10 @@ __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_
 #ifdef RT_DEBUG_COUNTERS
 __device__ unsigned long long g_dbg[16]; /* [k] rounds that picked phase k, [8+k] lanes that ran in them */
 #endif
-template <typename IO>
+template <bool SMEM, typename IO>
 __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_ops, uint32_t n, uint32_t *fetch, IO &io) {
     const uint32_t lane = threadIdx.x & 31u;
-    Traversal tr;
+    Traversal<SMEM> tr;
     SavedRays stk;
     bool active = false, exhausted = false;
     uint32_t idx = 0;
@@ -491,7 +550,7 @@ __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_
             case PH_SPHERE: tr.exec_sphere(ts); break;
             case PH_BOX: tr.exec_box(ts); break;
             case PH_TRI: tr.exec_tri(ts); break;
-            default: tr.exec_misc<true>(ts, stk, [&]() { return io.draw(); }); break;
+            default: tr.template exec_misc<true>(ts, stk, [&]() { return io.draw(); }); break;
             }
             if (tr.done()) {
                 io.store(idx, tr.best);
