@@ -79,13 +79,6 @@ __device__ __forceinline__ void load_slot8(const rtgpu_op *op, double d[8]) { /*
     d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y; d[4] = c.x; d[5] = c.y; d[6] = e.x; d[7] = e.y;
 }
 
-template <bool SMEM>
-__device__ __forceinline__ uint4 op_header(const struct TravScene &sc, uint32_t i);
-template <bool SMEM>
-__device__ __forceinline__ void op_payload(const struct TravScene &sc, uint32_t i, double d[6]);
-template <bool SMEM>
-__device__ __forceinline__ void op_slot8(const struct TravScene &sc, uint32_t i, double d[8]);
-
 /* ---- wrappers: ray into object space (hittable/mod.rs:166,240-248,322) -------------------- */
 __device__ __forceinline__ void xform_ray(const rtgpu_xform &xf, V3 &o, V3 &d) {
     switch (xf.kind) {
@@ -112,22 +105,8 @@ struct TravScene {
     const rtgpu_op *ops;
     const rtgpu_xform *xforms;
     const uint32_t *chain;
-    uint32_t sm_ops; /* shared-memory address of a staged copy of `ops` (SMEM variants), else 0 */
 };
-__device__ __forceinline__ TravScene trav_of(const DScene &sc, uint32_t sm_ops = 0) {
-    return TravScene{sc.ops, sc.xforms, sc.chain, sm_ops};
-}
-/* op fetch: from HBM/L2/L1 through the read-only path, or from the copy staged in shared memory */
-__device__ __forceinline__ uint4 lds_u128(uint32_t a) {
-    uint4 v;
-    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ double2 lds_f64x2(uint32_t a) {
-    double2 v;
-    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
-    return v;
-}
+__device__ __forceinline__ TravScene trav_of(const DScene &sc) { return TravScene{sc.ops, sc.xforms, sc.chain}; }
 __device__ __forceinline__ rtgpu_xform load_xform(const TravScene &sc, uint32_t chain_idx) {
     const rtgpu_xform *x = sc.xforms + __ldg(sc.chain + chain_idx);
     const double2 *p = reinterpret_cast<const double2 *>(x);
@@ -140,32 +119,9 @@ __device__ __forceinline__ rtgpu_xform load_xform(const TravScene &sc, uint32_t 
     return r;
 }
 
-template <bool SMEM>
-__device__ __forceinline__ uint4 op_header(const TravScene &sc, uint32_t i) {
-    if constexpr (SMEM) return lds_u128(sc.sm_ops + i * 64u);
-    else return load_op_header(sc.ops + i);
-}
-template <bool SMEM>
-__device__ __forceinline__ void op_payload(const TravScene &sc, uint32_t i, double d[6]) {
-    if constexpr (SMEM) {
-        uint32_t a = sc.sm_ops + i * 64u + 16u;
-        double2 x = lds_f64x2(a), y = lds_f64x2(a + 16u), z = lds_f64x2(a + 32u);
-        d[0] = x.x; d[1] = x.y; d[2] = y.x; d[3] = y.y; d[4] = z.x; d[5] = z.y;
-    } else {
-        load_op_payload(sc.ops + i, d);
-    }
-}
-template <bool SMEM>
-__device__ __forceinline__ void op_slot8(const TravScene &sc, uint32_t i, double d[8]) {
-    if constexpr (SMEM) {
-        uint32_t a = sc.sm_ops + i * 64u;
-        double2 x = lds_f64x2(a), y = lds_f64x2(a + 16u), z = lds_f64x2(a + 32u), w = lds_f64x2(a + 48u);
-        d[0] = x.x; d[1] = x.y; d[2] = y.x; d[3] = y.y; d[4] = z.x; d[5] = z.y; d[6] = w.x; d[7] = w.y;
-    } else {
-        load_slot8(sc.ops + i, d);
-    }
-}
-
+#ifndef RT_LEAF_INLINE
+#define RT_LEAF_INLINE __forceinline__
+#endif
 /* ---- primitive tests: return true and shrink `best` on a hit ------------------------------- */
 /* Sphere::hit, sphere.rs:39-56 (decision part; the record is rebuilt later for the winner) */
 __device__ __forceinline__ bool hit_sphere(V3 o, V3 d, double a, V3 c, double radius, double tmin, double &best) {
@@ -201,7 +157,7 @@ __device__ __forceinline__ bool hit_rect(V3 o, V3 d, double a0, double a1, doubl
     return true;
 }
 /* Boxes::hit = HittableList::hit over six rects (boxes.rs:24-69,82-84; hittable/mod.rs:90-100) */
-__device__ __forceinline__ bool hit_box(V3 o, V3 d, const double p[6], double tmin, double &best, uint32_t &face) {
+__device__ RT_LEAF_INLINE bool hit_box(V3 o, V3 d, const double p[6], double tmin, double &best, uint32_t &face) {
     bool any = false;
     if (hit_rect<2>(o, d, p[0], p[3], p[1], p[4], p[5], tmin, best)) { any = true; face = 0; }
     if (hit_rect<2>(o, d, p[0], p[3], p[1], p[4], p[2], tmin, best)) { any = true; face = 1; }
@@ -212,7 +168,7 @@ __device__ __forceinline__ bool hit_box(V3 o, V3 d, const double p[6], double tm
     return any;
 }
 /* Triangle::hit, triangle.rs:51-64 with inside() of :33-46; n is get_normal(), precomputed */
-__device__ __forceinline__ bool hit_triangle(V3 o, V3 d, V3 a, V3 b, V3 c, V3 n, double tmin, double &best) {
+__device__ RT_LEAF_INLINE bool hit_triangle(V3 o, V3 d, V3 a, V3 b, V3 c, V3 n, double tmin, double &best) {
     double t = dot(d, n);
     t = dot(a - o, n) / t;
     if (t != t || t < tmin || t > best) return false;
@@ -271,7 +227,6 @@ __device__ __forceinline__ void ray_state_derive(RayState &r) {
     r.sg.m = (r.inv.x < 0. ? 1u : 0u) | (r.inv.y < 0. ? 2u : 0u) | (r.inv.z < 0. ? 4u : 0u);
 }
 
-template <bool SMEM>
 __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm,
                                                      double tmin, double tmax);
 
@@ -290,7 +245,6 @@ struct SavedRays {
  * 128-bit loads issued together) is fetched as soon as the index is known; exec_*() consume it.
  * One call of exec handles one op, so a warp can run "all lanes that sit on a NODE" together,
  * then "all lanes that sit on a sphere", ... (see extend_warp_loop). */
-template <bool SMEM>
 struct Traversal {
     RayState r;
     double tm, tmin;
@@ -302,16 +256,14 @@ struct Traversal {
     /* the PUSH/POP stack lives OUTSIDE this struct (SavedRays): it is indexed dynamically, and an
      * aggregate with a dynamically indexed member is kept in local memory as a whole */
 
-    /* global variant: header + payload prefetched together (hides the L1/L2 latency behind the vote);
-     * shared variant: header now, payload at use (short live range, 12 registers fewer in the loop) */
+    /* header + payload are fetched together as soon as the index is known: the L1/L2 latency of the
+     * next op overlaps with the warp vote and with the other lanes' work */
     __device__ __forceinline__ void fetch_op(const TravScene sc) {
         if (i < end) {
-            h = op_header<SMEM>(sc, i);
-            if constexpr (!SMEM) op_payload<false>(sc, i, p);
+            const rtgpu_op *op = sc.ops + i;
+            h = load_op_header(op);
+            load_op_payload(op, p);
         }
-    }
-    __device__ __forceinline__ void need_payload(const TravScene sc) {
-        if constexpr (SMEM) op_payload<true>(sc, i, p);
     }
     __device__ __forceinline__ void start(const TravScene sc, uint32_t begin, uint32_t end_, V3 o, V3 d, double tm_, double tmin_,
                                           double tmax) {
@@ -332,17 +284,15 @@ struct Traversal {
     __device__ __forceinline__ uint32_t phase() const { return phase_of_kind(h.x & 0xffu); }
 
     __device__ __forceinline__ void exec_node(const TravScene sc) {
-        need_payload(sc);
         i = hit_aabb(r.o, r.inv, r.sg, p, tmin, best.t) ? i + 1 : h.y;
         fetch_op(sc);
     }
     __device__ __forceinline__ void exec_sphere(const TravScene sc) {
-        need_payload(sc);
         V3 c = v3(p[0], p[1], p[2]);
         uint32_t width = 1;
         if ((h.x & 0xffu) == RTGPU_OP_MSPHERE) { /* MovingSphere::center, sphere.rs:124-127 */
             double q[8];
-            op_slot8<SMEM>(sc, i + 1, q);
+            load_slot8(sc.ops + i + 1, q);
             c = c + (v3(q[0], q[1], q[2]) - c) * ((tm - p[4]) / (p[5] - p[4]));
             width = 2;
         }
@@ -351,15 +301,13 @@ struct Traversal {
         fetch_op(sc);
     }
     __device__ __forceinline__ void exec_box(const TravScene sc) {
-        need_payload(sc);
         if (hit_box(r.o, r.d, p, tmin, best.t, best.face)) best.op = i;
         i += 1;
         fetch_op(sc);
     }
     __device__ __forceinline__ void exec_tri(const TravScene sc) {
-        need_payload(sc);
         double q[8];
-        op_slot8<SMEM>(sc, i + 1, q);
+        load_slot8(sc.ops + i + 1, q);
         if (hit_triangle(r.o, r.d, v3(p[0], p[1], p[2]), v3(p[3], p[4], p[5]), v3(q[0], q[1], q[2]), v3(q[3], q[4], q[5]), tmin,
                          best.t))
             best.op = i;
@@ -369,7 +317,6 @@ struct Traversal {
     /* rects, ConstantMedium, PUSH, POP.  DRAW() = next uniform of the ray's stream */
     template <bool MAIN, typename DRAW>
     __device__ __forceinline__ void exec_misc(const TravScene sc, SavedRays &stk, DRAW &&draw) {
-        need_payload(sc);
         switch (h.x & 0xffu) {
         case RTGPU_OP_RECT_XY:
             if (hit_rect<2>(r.o, r.d, p[0], p[1], p[2], p[3], p[4], tmin, best.t)) best.op = i;
@@ -388,19 +335,19 @@ struct Traversal {
                 double t1 = CUDART_INF, t2 = CUDART_INF;
                 bool h1, h2 = false;
                 bool single_sphere = h.y == i + 2;
-                if (single_sphere) single_sphere = (op_header<SMEM>(sc, i + 1).x & 0xffu) == RTGPU_OP_SPHERE;
+                if (single_sphere) single_sphere = (load_op_header(sc.ops + i + 1).x & 0xffu) == RTGPU_OP_SPHERE;
                 if (single_sphere) { /* boundary = one Sphere (both media of final_scene) */
                     double bp[6];
-                    op_payload<SMEM>(sc, i + 1, bp);
+                    load_op_payload(sc.ops + i + 1, bp);
                     V3 c = v3(bp[0], bp[1], bp[2]);
                     h1 = hit_sphere(r.o, r.d, r.a(), c, bp[3], -CUDART_INF, t1);
                     if (h1) h2 = hit_sphere(r.o, r.d, r.a(), c, bp[3], t1 + 0.0001, t2);
                 } else {
-                    Closest r1 = closest_hit_boundary<SMEM>(sc, i + 1, h.y, r.o, r.d, tm, -CUDART_INF, CUDART_INF);
+                    Closest r1 = closest_hit_boundary(sc, i + 1, h.y, r.o, r.d, tm, -CUDART_INF, CUDART_INF);
                     h1 = r1.op != RT_NO_HIT;
                     t1 = r1.t;
                     if (h1) {
-                        Closest r2 = closest_hit_boundary<SMEM>(sc, i + 1, h.y, r.o, r.d, tm, t1 + 0.0001, CUDART_INF);
+                        Closest r2 = closest_hit_boundary(sc, i + 1, h.y, r.o, r.d, tm, t1 + 0.0001, CUDART_INF);
                         h2 = r2.op != RT_NO_HIT;
                         t2 = r2.t;
                     }
@@ -459,13 +406,12 @@ struct Traversal {
 };
 
 /* boundary walk of a medium whose boundary is not a single sphere: rare, kept out of line */
-template <bool SMEM>
 __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm,
                                                      double tmin, double tmax) {
-    Traversal<SMEM> tr;
+    Traversal tr;
     SavedRays stk;
     tr.start(sc, begin, end, o, d, tm, tmin, tmax);
-    while (!tr.done()) tr.template step<false>(sc, stk, []() { return 0.; });
+    while (!tr.done()) tr.step<false>(sc, stk, []() { return 0.; });
     return tr.best;
 }
 
@@ -488,10 +434,10 @@ __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_
 #ifdef RT_DEBUG_COUNTERS
 __device__ unsigned long long g_dbg[16]; /* [k] rounds that picked phase k, [8+k] lanes that ran in them */
 #endif
-template <bool SMEM, typename IO>
+template <typename IO>
 __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_ops, uint32_t n, uint32_t *fetch, IO &io) {
     const uint32_t lane = threadIdx.x & 31u;
-    Traversal<SMEM> tr;
+    Traversal tr;
     SavedRays stk;
     bool active = false, exhausted = false;
     uint32_t idx = 0;
@@ -550,7 +496,7 @@ __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_
             case PH_SPHERE: tr.exec_sphere(ts); break;
             case PH_BOX: tr.exec_box(ts); break;
             case PH_TRI: tr.exec_tri(ts); break;
-            default: tr.template exec_misc<true>(ts, stk, [&]() { return io.draw(); }); break;
+            default: tr.exec_misc<true>(ts, stk, [&]() { return io.draw(); }); break;
             }
             if (tr.done()) {
                 io.store(idx, tr.best);

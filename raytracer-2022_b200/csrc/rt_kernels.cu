@@ -141,28 +141,7 @@ __global__ void __launch_bounds__(kThreads, RT_EXTEND_MIN_BLOCKS) k_extend(DScen
     io.q = q;
     io.hb = hb;
     io.wp = wp;
-    extend_warp_loop<false>(trav_of(sc), sc.n_ops, *count, fetch, io);
-}
-
-/* Variant for programs that fit in shared memory (every BASELINE config except the 13 079-triangle mesh):
- * one 512-thread block per SM copies the whole traversal program into shared memory once (coalesced
- * 128-bit loads), then every op fetch of the walk is an LDS instead of an L1/L2 access. */
-constexpr int kSmemThreads = 512;
-__device__ __forceinline__ uint32_t stage_ops_in_smem(const DScene &sc) {
-    extern __shared__ uint4 smem_ops[];
-    const uint4 *src = reinterpret_cast<const uint4 *>(sc.ops);
-    for (uint32_t k = threadIdx.x; k < sc.n_ops * 4u; k += blockDim.x) smem_ops[k] = __ldg(src + k);
-    __syncthreads();
-    return (uint32_t)__cvta_generic_to_shared(smem_ops);
-}
-__global__ void __launch_bounds__(kSmemThreads, 1) k_extend_smem(DScene sc, PathQueue q, HitBuf hb, const uint32_t *count, uint32_t *fetch,
-                                                                 WaveParams wp) {
-    uint32_t sm = stage_ops_in_smem(sc);
-    QueueIO io;
-    io.q = q;
-    io.hb = hb;
-    io.wp = wp;
-    extend_warp_loop<true>(trav_of(sc, sm), sc.n_ops, *count, fetch, io);
+    extend_warp_loop(trav_of(sc), sc.n_ops, *count, fetch, io);
 }
 
 /* ---- shading, split by material class ------------------------------------------------------------
@@ -482,18 +461,7 @@ __global__ void __launch_bounds__(kThreads, RT_EXTEND_MIN_BLOCKS) k_trace_extend
     io.t = t;
     io.op = op;
     io.rng_pos = rng_pos;
-    extend_warp_loop<false>(trav_of(sc), sc.n_ops, n, fetch, io);
-}
-__global__ void __launch_bounds__(kSmemThreads, 1) k_trace_extend_smem(DScene sc, const rtgpu_ray *rays, const uint64_t *keys, double *t,
-                                                                       uint32_t *op, uint32_t *rng_pos, uint32_t n, uint32_t *fetch) {
-    uint32_t sm = stage_ops_in_smem(sc);
-    BatchIO io;
-    io.rays = rays;
-    io.keys = keys;
-    io.t = t;
-    io.op = op;
-    io.rng_pos = rng_pos;
-    extend_warp_loop<true>(trav_of(sc, sm), sc.n_ops, n, fetch, io);
+    extend_warp_loop(trav_of(sc), sc.n_ops, n, fetch, io);
 }
 __global__ void __launch_bounds__(kThreads) k_trace_record(DScene sc, const rtgpu_ray *rays, const double *t, const uint32_t *op,
                                                            const uint32_t *rng_pos, rtgpu_hit *out, uint32_t n) {
@@ -607,7 +575,6 @@ struct rtgpu_scene : WaveRes {
     std::vector<void *> allocs;
     const uint8_t *mat_class = nullptr; /* device: shade class per material */
     bool class_present[8] = {true, false, false, false, false, false, false, false};
-    size_t smem_bytes = 0; /* > 0: the traversal program is staged in shared memory (k_extend_smem) */
     int sort_mode = 0; /* RTGPU_SORT_RAYS=1: reorder rays between bounces */
     uint32_t sort_min = 1u << 16;
 };
@@ -812,10 +779,8 @@ rtgpu_status run_wave(rtgpu_scene *s, const WaveParams &wp, int max_depth, cudaS
         }
         PathQueue &qin = s->q[cur], &qout = s->q[cur ^ 1];
         if (timing) CK(cudaEventRecord(s->events[ev++], stream));
-        if (s->smem_bytes)
-            k_extend_smem<<<kSMs, kSmemThreads, s->smem_bytes, stream>>>(s->d, qin, s->hb, s->counts + b, s->counts + s->max_counts + b, wp);
-        else
-            k_extend<<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->counts + b, s->counts + s->max_counts + b, wp);
+        k_extend<<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->counts + b, s->counts + s->max_counts + b, wp);
+        CK(cudaGetLastError()); /* a failed extend launch must not let the shade kernels read stale hits */
         if (timing) CK(cudaEventRecord(s->events[ev++], stream));
         {
             uint32_t *cc = s->class_count + 8 * b;
@@ -962,18 +927,6 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
 #undef UP
     s->d.n_ops = desc->n_ops;
     s->d.n_lights = desc->n_lights;
-    {
-        size_t need = (size_t)desc->n_ops * sizeof(rtgpu_op);
-        const char *e = getenv("RTGPU_SMEM_OPS");
-        bool want = !e || atoi(e) != 0;
-        if (want && need <= 200 * 1024) {
-            /* the attribute is per function, not per launch: always allow the largest program we stage */
-            cudaError_t e1 = cudaFuncSetAttribute(k_extend_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            cudaError_t e2 = cudaFuncSetAttribute(k_trace_extend_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (e1 == cudaSuccess && e2 == cudaSuccess) s->smem_bytes = need;
-            else cudaGetLastError();
-        }
-    }
     s->d.cam = desc->camera;
     for (int c = 0; c < 3; ++c) s->d.background[c] = desc->background[c];
     *out = s;
@@ -1120,10 +1073,7 @@ rtgpu_status rtgpu_trace_batch(rtgpu_scene *s, const rtgpu_ray *rays, int64_t n,
         CK(cudaEventCreate(&e0));
         CK(cudaEventCreate(&e1));
         CK(cudaEventRecord(e0, 0));
-        if (s->smem_bytes)
-            k_trace_extend_smem<<<kSMs, kSmemThreads, s->smem_bytes>>>(s->d, d_rays, d_keys, d_t, d_u32, d_u32 + n, (uint32_t)n, d_u32 + 2 * n);
-        else
-            k_trace_extend<<<grid_blocks(), kThreads>>>(s->d, d_rays, d_keys, d_t, d_u32, d_u32 + n, (uint32_t)n, d_u32 + 2 * n);
+        k_trace_extend<<<grid_blocks(), kThreads>>>(s->d, d_rays, d_keys, d_t, d_u32, d_u32 + n, (uint32_t)n, d_u32 + 2 * n);
         CK(cudaEventRecord(e1, 0));
         k_trace_record<<<grid_blocks(), kThreads>>>(s->d, d_rays, d_t, d_u32, d_u32 + n, d_out, (uint32_t)n);
         CK(cudaGetLastError());
