@@ -269,7 +269,7 @@ def main():
             g.close()
             return st
 
-        for _ in range(min(args.warmup, 2)):
+        for _ in range(max(args.warmup, 3)):  # the first scene re-creations also warm the parked-buffer path
             e2e_step()
         sync()
         k_e2e = max(1, min(args.steps, 5))
