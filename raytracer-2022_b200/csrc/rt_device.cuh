@@ -418,8 +418,11 @@ __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_
 #ifndef RT_EXTEND_REFILL
 #define RT_EXTEND_REFILL 8 /* refill when at least this many lanes of the warp are idle */
 #endif
+#ifndef RT_NODE_UNROLL
+#define RT_NODE_UNROLL 2 /* boxes a lane may test under one vote (A/B on the B200: 2 is +2..7 %) */
+#endif
 #ifndef RT_NODE_QUORUM_PCT
-#define RT_NODE_QUORUM_PCT 25 /* keep running NODE rounds while at least this share of the live lanes sits on a NODE */
+#define RT_NODE_QUORUM_PCT 35 /* keep running NODE rounds while at least this share of the live lanes sits on a NODE */
 #endif
 
 /* The extend loop of one warp (persistent): every lane owns one ray at a time.
@@ -481,6 +484,12 @@ __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_
             if ((uint32_t)__popc(m) < node_quorum) break;
             if (in_node) {
                 tr.exec_node(ts);
+#if RT_NODE_UNROLL >= 2
+                if (!tr.done() && tr.phase() == PH_NODE) tr.exec_node(ts); /* second box under the same vote */
+#endif
+#if RT_NODE_UNROLL >= 3
+                if (!tr.done() && tr.phase() == PH_NODE) tr.exec_node(ts);
+#endif
                 if (tr.done()) {
                     io.store(idx, tr.best);
                     active = false;
