@@ -418,6 +418,9 @@ __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_
 #ifndef RT_EXTEND_REFILL
 #define RT_EXTEND_REFILL 8 /* refill when at least this many lanes of the warp are idle */
 #endif
+#ifndef RT_MEDIUM_QUORUM
+#define RT_MEDIUM_QUORUM 8 /* lanes that must stand on a ConstantMedium before it runs (1 = no hold) */
+#endif
 #ifndef RT_NODE_UNROLL
 #define RT_NODE_UNROLL 2 /* boxes a lane may test under one vote (A/B on the B200: 2 is +2..7 %) */
 #endif
@@ -471,6 +474,7 @@ __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_
          * leaf op once (plain SIMT over the few leaf kinds) and the cycle repeats. */
         const uint32_t n_active = 32u - (uint32_t)__popc(idle);
         const uint32_t node_quorum = max(1u, (n_active * RT_NODE_QUORUM_PCT) / 100u);
+        bool node_ran = false;
 #pragma unroll 1
         for (;;) {
             bool in_node = active && tr.phase() == PH_NODE;
@@ -482,6 +486,7 @@ __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_
             }
 #endif
             if ((uint32_t)__popc(m) < node_quorum) break;
+            node_ran = true;
             if (in_node) {
                 tr.exec_node(ts);
 #if RT_NODE_UNROLL >= 2
@@ -496,7 +501,23 @@ __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_
                 }
             }
         }
-        if (active) {
+        /* expensive leaves are held back until enough lanes want the same code: a ConstantMedium costs ~300
+         * instructions (two boundary hits, Philox, log) and every ray of a foggy scene meets it, so the
+         * lanes standing on one pile up quickly; they run together instead of 5 at a time. */
+        bool hold = false;
+#if RT_MEDIUM_QUORUM > 1
+        {
+            bool at_medium = active && (tr.h.x & 0xffu) == RTGPU_OP_MEDIUM;
+            uint32_t mm = __ballot_sync(0xffffffffu, at_medium);
+            if (mm) {
+                /* hold only while something else certainly advances this iteration (a NODE round ran, or another
+                 * lane runs a different leaf below); lanes on a NODE under the node quorum do NOT count */
+                uint32_t other_leaf = __ballot_sync(0xffffffffu, active && !at_medium && tr.phase() != PH_NODE);
+                hold = at_medium && (uint32_t)__popc(mm) < (uint32_t)RT_MEDIUM_QUORUM && (node_ran || other_leaf != 0u);
+            }
+        }
+#endif
+        if (active && !hold) {
 #ifdef RT_DEBUG_COUNTERS
             atomicAdd(&g_dbg[tr.phase()], 1ull);
 #endif
