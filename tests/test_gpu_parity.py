@@ -37,11 +37,15 @@ def compare_hits(g, o, rel=1e-5, exact_geometry=False):
     t_o, t_g = o["t"][m], g["t"][m]
     # a NaN t is a legal result upstream (aarect.rs lets 0/0 through, Q2): it must be NaN on both sides
     assert np.array_equal(np.isnan(t_o), np.isnan(t_g))
-    fin = ~np.isnan(t_o)
+    fin = np.isfinite(t_o)
+    assert np.array_equal(t_g[~fin & ~np.isnan(t_o)], t_o[~fin & ~np.isnan(t_o)])  # +-inf must be equal as such
     assert np.all(np.abs(t_g - t_o)[fin] <= rel * np.abs(t_o)[fin])
-    scale = np.maximum(np.abs(o["p"][m]).max(axis=1, keepdims=True), 1e-300)
-    assert np.all((np.abs(g["p"][m] - o["p"][m]) <= rel * scale)[fin])
-    assert np.all((np.abs(g["n"][m] - o["n"][m]) <= rel)[fin])
+    pfin = fin & np.isfinite(o["p"][m]).all(axis=1)
+    with np.errstate(invalid="ignore"):
+        scale = np.maximum(np.abs(o["p"][m]).max(axis=1, keepdims=True), 1e-300)
+        assert np.all((np.abs(g["p"][m] - o["p"][m]) <= rel * scale)[pfin])
+        assert np.all((np.abs(g["n"][m] - o["n"][m]) <= rel)[pfin])
+    assert np.array_equal(np.isnan(g["p"][m]), np.isnan(o["p"][m]))
     ok = np.isfinite(o["u"][m]) & np.isfinite(o["v"][m])
     assert np.all(np.abs(g["u"][m][ok] - o["u"][m][ok]) <= 1e-9)
     assert np.all(np.abs(g["v"][m][ok] - o["v"][m][ok]) <= 1e-9)
@@ -242,3 +246,49 @@ def test_invalid_inputs_return_errors():
     s2 = rt.Scene(seed=1)
     with pytest.raises(rt.RtError):
         s2.bvh_node([])  # BvhNode::new_vec panics on an empty vec (bvh/mod.rs:41-43)
+
+
+def test_edge_cases_empty_and_degenerate():
+    s, orc, gpu = get("cornell_box")
+    # empty batch
+    out, ms = gpu.trace_batch(np.zeros(0, dtype=rt.RAY_DTYPE))
+    assert out.shape == (0,)
+    # empty spp range: accumulation buffer is zeroed, no rays
+    a, st = gpu.render(16, 16, 5, 5)
+    assert st.rays == 0 and st.samples == 0 and not a.any()
+    # depth 0 -> black (main.rs:240-242), depth 1 -> only camera rays
+    a0, st0 = gpu.render(16, 16, 0, 2, max_depth=0)
+    assert st0.rays == 0 and not a0.any()
+    a1, st1 = gpu.render(16, 16, 0, 2, max_depth=1)
+    r1, o1 = orc.render(16, 16, 0, 2, max_depth=1, threads=2)
+    assert st1.rays == o1.rays == 16 * 16 * 2 and np.allclose(a1, r1, rtol=1e-6, atol=1e-7)
+    # smallest legal image (u = (x + xi)/(W-1) needs W, H >= 2)
+    a2, st2 = gpu.render(2, 2, 0, 4)
+    r2, _ = orc.render(2, 2, 0, 4, threads=1)
+    assert np.allclose(a2, r2, rtol=1e-5, atol=1e-6)
+    # rays with zero direction components, infinite/NaN inputs: same answers as the oracle
+    rays = make_rays([(278, 278, -800), (278, 554, 179), (0, 0, 0), (278, 278, 278), (278, 278, 278), (278, 278, 278)],
+                     [(0, 0, 1), (1, 0, 0), (0, 0, 0), (np.inf, 0, 1), (np.nan, 1, 0), (1e-320, 1, 1e-320)])
+    compare_hits(gpu.trace_batch(rays)[0], orc.trace_batch(rays))
+    # a world that is a bare list with an empty sub-list, and a world that nothing can hit
+    def build(s):
+        m = s.lambertian((0.5, 0.5, 0.5))
+        return [s.hittable_list([]), s.sphere((0, 0, 5), 1.0, m), s.hittable_list([s.hittable_list([])])]
+    s2, orc2, gpu2 = unit_scene(build)
+    rays = make_rays([(0, 0, 0), (0, 0, 0)], [(0, 0, 1), (0, 0, -1)])
+    g = gpu2.trace_batch(rays)[0]
+    compare_hits(g, orc2.trace_batch(rays))
+    assert g["hit"].tolist() == [1, 0]
+
+
+def test_c5_resolution_smoke():
+    """config 5 is config 3 at 3840x2160: one sample per pixel renders and matches the oracle on a crop"""
+    s = rt.Scene(seed=2022).build_config("final_scene", 3840 / 2160)
+    gpu = rt.GpuScene(s.lower(), device=0)
+    a, st = gpu.render(3840, 2160, 0, 1, seed=9)
+    assert st.samples == 3840 * 2160 and st.rays > st.samples
+    orc = OracleScene(s)
+    ref, _ = orc.render(3840, 2160, 0, 1, seed=9, threads=16, region=(1000, 1064, 500, 532))
+    crop_g, crop_o = a[500:532, 1000:1064].astype(np.float64), ref[500:532, 1000:1064]
+    close = np.abs(crop_g - crop_o).max(axis=2) <= 1e-5 * np.maximum(1.0, np.abs(crop_o).max(axis=2))
+    assert close.mean() > 0.97
