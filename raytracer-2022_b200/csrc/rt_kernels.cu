@@ -588,16 +588,21 @@ bool g_parked_valid[kMaxDevices];
 
 namespace {
 
-template <typename T>
-rtgpu_status upload(rtgpu_scene *s, const T *src, size_t n, const T **dst) {
-    void *p = nullptr;
-    size_t bytes = (n ? n : 1) * sizeof(T);
-    CK(cudaMalloc(&p, bytes));
-    s->allocs.push_back(p);
-    if (n) CK(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
-    *dst = reinterpret_cast<const T *>(p);
-    return RTGPU_OK;
-}
+/* Scene arrays are staged into ONE host blob and copied with ONE cudaMemcpy into ONE allocation
+ * (256-byte aligned sub-arrays): scene creation costs one malloc + one copy instead of eleven. */
+struct SceneArena {
+    std::vector<unsigned char> host;
+    std::vector<std::pair<size_t, const void **>> fix; /* offset -> device pointer to patch */
+    template <typename T>
+    void add(const T *src, size_t n, const T **dst) {
+        size_t off = (host.size() + 255) & ~(size_t)255;
+        size_t bytes = (n ? n : 1) * sizeof(T);
+        host.resize(off + bytes, 0);
+        if (n) memcpy(host.data() + off, src, n * sizeof(T));
+        fix.emplace_back(off, reinterpret_cast<const void **>(dst));
+    }
+    rtgpu_status commit(rtgpu_scene *s);
+};
 
 rtgpu_status validate(const rtgpu_scene_desc *d) {
     auto bad = [](const char *m) {
@@ -663,6 +668,23 @@ rtgpu_status validate(const rtgpu_scene_desc *d) {
     }
     for (uint32_t i = 0; i < d->n_lights; ++i)
         if (d->lights[i].kind > RTGPU_LIGHT_DEAD) return bad("unknown light kind");
+    return RTGPU_OK;
+}
+
+rtgpu_status SceneArena::commit(rtgpu_scene *s) {
+    void *p = nullptr;
+    {
+        /* stream-ordered pool, kept warm: re-creating a scene every frame reuses the same block */
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, s->device));
+        uint64_t keep = ~0ull;
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    CK(cudaMallocAsync(&p, host.size(), 0));
+    s->allocs.push_back(p);
+    CK(cudaMemcpyAsync(p, host.data(), host.size(), cudaMemcpyHostToDevice, 0));
+    CK(cudaStreamSynchronize(0));
+    for (auto &f : fix) *f.second = static_cast<unsigned char *>(p) + f.first;
     return RTGPU_OK;
 }
 
@@ -883,22 +905,17 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
     if (const char *e = getenv("RTGPU_SORT_RAYS")) s->sort_mode = atoi(e);
     if (const char *e = getenv("RTGPU_SORT_MIN")) s->sort_min = (uint32_t)atoll(e);
     memset(&s->d, 0, sizeof s->d);
-#define UP(field, src, n)                                                                                          \
-    st = upload(s, src, (size_t)(n), &s->d.field);                                                                 \
-    if (st != RTGPU_OK) {                                                                                          \
-        rtgpu_scene_destroy(s);                                                                                    \
-        return st;                                                                                                 \
-    }
-    UP(ops, desc->ops, desc->n_ops)
-    UP(xforms, desc->xforms, desc->n_xforms)
-    UP(chain, desc->chain, desc->n_chain)
-    UP(ctxs, desc->ctxs, desc->n_ctxs)
-    UP(mats, desc->materials, desc->n_materials)
-    UP(texs, desc->textures, desc->n_textures)
-    UP(perlins, desc->perlins, desc->n_perlins)
-    UP(images, desc->images, desc->n_images)
-    UP(texels, desc->texels, desc->n_texel_bytes)
-    UP(lights, desc->lights, desc->n_lights)
+    SceneArena arena;
+    arena.add(desc->ops, desc->n_ops, &s->d.ops);
+    arena.add(desc->xforms, desc->n_xforms, &s->d.xforms);
+    arena.add(desc->chain, desc->n_chain, &s->d.chain);
+    arena.add(desc->ctxs, desc->n_ctxs, &s->d.ctxs);
+    arena.add(desc->materials, desc->n_materials, &s->d.mats);
+    arena.add(desc->textures, desc->n_textures, &s->d.texs);
+    arena.add(desc->perlins, desc->n_perlins, &s->d.perlins);
+    arena.add(desc->images, desc->n_images, &s->d.images);
+    arena.add(desc->texels, (size_t)desc->n_texel_bytes, &s->d.texels);
+    arena.add(desc->lights, desc->n_lights, &s->d.lights);
     {
         /* shade class per material (see k_classify) */
         std::vector<uint8_t> mc(desc->n_materials ? desc->n_materials : 1, 2);
@@ -918,13 +935,13 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
             }
             s->class_present[mc[i]] = true;
         }
-        st = upload(s, mc.data(), mc.size(), &s->mat_class);
-        if (st != RTGPU_OK) {
-            rtgpu_scene_destroy(s);
-            return st;
-        }
+        arena.add(mc.data(), mc.size(), &s->mat_class);
     }
-#undef UP
+    st = arena.commit(s);
+    if (st != RTGPU_OK) {
+        rtgpu_scene_destroy(s);
+        return st;
+    }
     s->d.n_ops = desc->n_ops;
     s->d.n_lights = desc->n_lights;
     s->d.cam = desc->camera;
@@ -936,7 +953,7 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
 rtgpu_status rtgpu_scene_destroy(rtgpu_scene *s) {
     if (!s) return RTGPU_OK;
     cudaSetDevice(s->device);
-    for (void *p : s->allocs) cudaFree(p);
+    for (void *p : s->allocs) cudaFreeAsync(p, 0);
     {
         std::lock_guard<std::mutex> lock(g_park_mutex);
         WaveRes &w = *s;
