@@ -302,11 +302,12 @@ def main():
         peak, peak_src = measured_peaks()
         value = rays_all / ms / 1e3  # Mrays/s
         ext_gbs = rays * EXTEND_BYTES_PER_RAY / (ms_extend * 1e-3) / 1e9 if ms_extend > 0 else None
-        traffic = None
+        traffic = traffic_rays = None
         rj = os.path.join(ROOT, "profiles", "roofline_ncu.json")
         if os.path.exists(rj):
             try:
-                traffic = json.load(open(rj)).get("k_extend_dram_bytes_per_launch")
+                tj = json.load(open(rj))
+                traffic, traffic_rays = tj.get("k_extend_dram_bytes_per_launch"), tj.get("captured_launch_rays")
             except Exception:
                 traffic = None
         line = {
@@ -324,6 +325,8 @@ def main():
             "roofline": {
                 "bound": "hbm", "kernel": "k_extend", "achieved": ext_gbs, "peak": peak, "unit": "GB/s",
                 "frac": (ext_gbs / peak) if ext_gbs else None, "traffic": traffic, "peak_source": peak_src,
+                "traffic_note": (f"ncu dram bytes of ONE captured launch with {traffic_rays} rays (bounce 1 of a wave); its algorithmic "
+                                 f"bytes are {traffic_rays * EXTEND_BYTES_PER_RAY}" if traffic_rays else None),
                 "bytes_per_ray": EXTEND_BYTES_PER_RAY, "avg_launch_ms": ms_extend / max(launches_extend, 1),
                 "rays_per_launch": rays / max(launches_extend, 1),
                 "extend_share_of_step": ms_extend / (ms if world == 1 else max(ms, 1e-9)),
