@@ -65,7 +65,8 @@ enum rt_object_kind {
     RT_OBJ_FLIP_FACE = 10,    /* hittable/mod.rs:275 c0 = child                                   */
     RT_OBJ_ZOOM = 11,         /* hittable/mod.rs:303 c0 = child, p[0] = rate                      */
     RT_OBJ_BVH_NODE = 12,     /* bvh/mod.rs:34       c0 = left, c1 = right, p[0..5] = box         */
-    RT_OBJ_LIST = 13          /* hittable/mod.rs:75  c0 = first index into list_items, c1 = count */
+    RT_OBJ_LIST = 13,         /* hittable/mod.rs:75  c0 = first index into list_items, c1 = count */
+    RT_OBJ_RING = 14          /* ring.rs:22          p = r t; annulus in the y = 0 plane, radii r-t .. r+t         */
 };
 typedef struct rt_object {
     int32_t kind;

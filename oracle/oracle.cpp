@@ -850,6 +850,40 @@ struct Triangle : Hittable {
     }
 };
 
+// hittable/ring.rs
+struct Ring : Hittable {
+    double r, t, dis_min, dis_max;
+    const Material *mat;
+    Ring(double r_, double t_, const Material *m) : r(r_), t(t_), mat(m) { // :22-30
+        dis_min = (r - t) * (r - t);
+        dis_max = (r + t) * (r + t);
+    }
+    bool hit(const Ray &ray, double t_min, double t_max, HitRecord &rec) const override { // :34-52
+        double tt = -ray.orig.y / ray.dir.y;
+        if (tt != tt || tt < t_min || tt > t_max) return false;
+        Point3 p = ray.at(tt);
+        double d = p.x * p.x + p.z * p.z;
+        if (d < dis_min || d > dis_max) return false;
+        rec = HitRecord();
+        rec.p = p;
+        rec.normal = Vec3(0., 1., 0.);
+        rec.t = tt;
+        rec.u = 0.;
+        rec.v = 0.;
+        rec.front_face = false;
+        rec.mat_ptr = mat;
+        rec.gid = gid;
+        rec.set_face_normal(ray, Vec3(0., 1., 0.));
+        return true;
+    }
+    bool bounding_box(double, double, AABB &out) const override { // :54-62
+        double thickness = 0.0001;
+        double rr = r + t;
+        out = AABB(Point3(-rr, -thickness, -rr), Point3(rr, thickness, rr));
+        return true;
+    }
+};
+
 // hittable/constantmedium.rs
 struct ConstantMedium : Hittable {
     HittablePtr boundary;
@@ -1152,6 +1186,9 @@ HittablePtr build_object(orc_scene &s, int id, int depth = 0) {
         out = h;
         break;
     }
+    case RT_OBJ_RING:
+        out = std::make_shared<Ring>(p[0], p[1], build_material(s, o.mat));
+        break;
     case RT_OBJ_MEDIUM: {
         auto h = std::make_shared<ConstantMedium>();
         h->boundary = build_object(s, o.c0, depth + 1);

@@ -199,6 +199,9 @@ class Scene:
     def triangle(self, a, b, c, mat):
         return self._obj(D.OBJ_TRIANGLE, mat, -1, -1, list(a) + list(b) + list(c))
 
+    def ring(self, r, t, mat):
+        return self._obj(D.OBJ_RING, mat, -1, -1, [r, t])
+
     def constant_medium(self, boundary, density, albedo):
         return self._obj(D.OBJ_MEDIUM, self.isotropic(albedo), boundary, -1, [density])
 

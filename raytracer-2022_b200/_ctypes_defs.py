@@ -169,7 +169,7 @@ assert C.sizeof(rtgpu_op) == 64
 TEX_SOLID, TEX_CHECKER, TEX_NOISE, TEX_IMAGE = range(4)
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_DIFFUSE_LIGHT, MAT_ISOTROPIC = range(5)
 (OBJ_SPHERE, OBJ_MOVING_SPHERE, OBJ_XY_RECT, OBJ_XZ_RECT, OBJ_YZ_RECT, OBJ_BOX, OBJ_TRIANGLE, OBJ_MEDIUM,
- OBJ_TRANSLATE, OBJ_ROTATE_Y, OBJ_FLIP_FACE, OBJ_ZOOM, OBJ_BVH_NODE, OBJ_LIST) = range(14)
+ OBJ_TRANSLATE, OBJ_ROTATE_Y, OBJ_FLIP_FACE, OBJ_ZOOM, OBJ_BVH_NODE, OBJ_LIST, OBJ_RING) = range(15)
 (OP_NODE, OP_SPHERE, OP_MSPHERE, OP_RECT_XY, OP_RECT_XZ, OP_RECT_YZ, OP_BOX, OP_TRI, OP_MEDIUM, OP_PUSH,
- OP_POP) = range(11)
+ OP_POP, OP_RING) = range(12)
 RTGPU_OK, RTGPU_ERR_INVALID_SCENE, RTGPU_ERR_INVALID_ARG, RTGPU_ERR_CUDA, RTGPU_ERR_OOM = range(5)

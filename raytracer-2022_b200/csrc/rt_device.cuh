@@ -156,6 +156,16 @@ __device__ __forceinline__ bool hit_rect(V3 o, V3 d, double a0, double a1, doubl
     best = t;
     return true;
 }
+/* Ring::hit, ring.rs:34-46: annulus in the plane y = 0 */
+__device__ __forceinline__ bool hit_ring(V3 o, V3 d, double dis_min, double dis_max, double tmin, double &best) {
+    double t = -o.y / d.y;
+    if (t != t || t < tmin || t > best) return false;
+    V3 p = o + d * t;
+    double dd = p.x * p.x + p.z * p.z;
+    if (dd < dis_min || dd > dis_max) return false;
+    best = t;
+    return true;
+}
 /* Boxes::hit = HittableList::hit over six rects (boxes.rs:24-69,82-84; hittable/mod.rs:90-100) */
 __device__ RT_LEAF_INLINE bool hit_box(V3 o, V3 d, const double p[6], double tmin, double &best, uint32_t &face) {
     bool any = false;
@@ -233,8 +243,8 @@ __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_
 /* phases of the warp scheduler: ops whose code is the same run together */
 enum { PH_NODE = 0, PH_SPHERE = 1, PH_BOX = 2, PH_TRI = 3, PH_MISC = 4, PH_COUNT = 5, PH_NONE = 7 };
 __device__ __forceinline__ uint32_t phase_of_kind(uint32_t kind) {
-    /* NODE SPHERE MSPHERE RECT_XY RECT_XZ RECT_YZ BOX TRI MEDIUM PUSH POP, 3 bits each */
-    return (uint32_t)((044432444110ull >> (3 * kind)) & 7ull);
+    /* NODE SPHERE MSPHERE RECT_XY RECT_XZ RECT_YZ BOX TRI MEDIUM PUSH POP RING, 3 bits each */
+    return (uint32_t)((0444432444110ull >> (3 * kind)) & 7ull);
 }
 
 struct SavedRays {
@@ -328,6 +338,10 @@ struct Traversal {
             break;
         case RTGPU_OP_RECT_YZ:
             if (hit_rect<0>(r.o, r.d, p[0], p[1], p[2], p[3], p[4], tmin, best.t)) best.op = i;
+            i += 1;
+            break;
+        case RTGPU_OP_RING:
+            if (hit_ring(r.o, r.d, p[0], p[1], tmin, best.t)) best.op = i;
             i += 1;
             break;
         case RTGPU_OP_MEDIUM:
@@ -614,6 +628,12 @@ __device__ __noinline__ void make_record(const DScene &sc, const Ray &wr, double
     case RTGPU_OP_RECT_XY: rect_record<2>(rec, o, d, p[0], p[1], p[2], p[3], t); break;
     case RTGPU_OP_RECT_XZ: rect_record<1>(rec, o, d, p[0], p[1], p[2], p[3], t); break;
     case RTGPU_OP_RECT_YZ: rect_record<0>(rec, o, d, p[0], p[1], p[2], p[3], t); break;
+    case RTGPU_OP_RING: /* ring.rs:48-51 */
+        rec.p = o + d * t;
+        rec.u = 0.;
+        rec.v = 0.;
+        set_face_normal(rec, d, v3(0., 1., 0.));
+        break;
     case RTGPU_OP_BOX:
         rec.face = (int32_t)face;
         switch (face) { /* boxes.rs:24-69 */

@@ -638,7 +638,7 @@ rtgpu_status validate(const rtgpu_scene_desc *d) {
             if (--push < 0) return bad("POP without PUSH");
             break;
         default:
-            if (kind > RTGPU_OP_POP) return bad("unknown op kind");
+            if (kind > RTGPU_OP_RING) return bad("unknown op kind");
             break;
         }
         if (kind != RTGPU_OP_NODE && kind != RTGPU_OP_PUSH && kind != RTGPU_OP_POP) {

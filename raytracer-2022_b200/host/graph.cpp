@@ -138,6 +138,11 @@ int32_t Scene::add_object(int kind, int mat, int c0, int c1, const double *p, in
         check_mat(mat);
         o.c0 = o.c1 = -1;
         break;
+    case RT_OBJ_RING:
+        need(2);
+        check_mat(mat);
+        o.c0 = o.c1 = -1;
+        break;
     case RT_OBJ_MEDIUM:
         need(1);
         check_obj(c0);
@@ -323,6 +328,11 @@ bool Scene::bounding_box(int32_t id, double time0, double time1, Box3 &out) cons
             out.mx[c] = std::fmax(p[c], std::fmax(p[3 + c], p[6 + c]));
         }
         return true;
+    case RT_OBJ_RING: { // ring.rs:54-62
+        double rr = p[0] + p[1];
+        set(-rr, -0.0001, -rr, rr, 0.0001, rr);
+        return true;
+    }
     case RT_OBJ_MEDIUM: // constantmedium.rs:46-48
     case RT_OBJ_FLIP_FACE: // hittable/mod.rs:289-291
         return bounding_box(o.c0, time0, time1, out);
@@ -532,6 +542,10 @@ Obj Boxes::new_(Scene &s, Point3 p0, Point3 p1, Mat m) {
 Obj Triangle::new_(Scene &s, Point3 a, Point3 b, Point3 c, Mat m) {
     double p[9] = {a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z};
     return Obj{s.add_object(RT_OBJ_TRIANGLE, m.id, -1, -1, p, 9)};
+}
+Obj Ring::new_(Scene &s, double r, double t, Mat m) {
+    double p[2] = {r, t};
+    return Obj{s.add_object(RT_OBJ_RING, m.id, -1, -1, p, 2)};
 }
 Obj ConstantMedium::new_(Scene &s, Obj boundary, double d, Color c) { return new_arc(s, boundary, d, SolidColor::new_(s, c)); }
 Obj ConstantMedium::new_arc(Scene &s, Obj boundary, double d, Tex a) {

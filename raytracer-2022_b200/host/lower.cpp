@@ -142,6 +142,12 @@ struct Lowerer {
             push_raw(s1);
             break;
         }
+        case RT_OBJ_RING: {
+            uint32_t i = push_op(RTGPU_OP_RING, current_ctx(), mat_of(o), (uint32_t)id);
+            out.ops[i].d[0] = (p[0] - p[1]) * (p[0] - p[1]); // dis_min, ring.rs:27
+            out.ops[i].d[1] = (p[0] + p[1]) * (p[0] + p[1]); // dis_max, ring.rs:28
+            break;
+        }
         case RT_OBJ_MEDIUM: {
             if (in_boundary) throw Error{"lower: a ConstantMedium inside a ConstantMedium boundary is not supported"};
             uint32_t i = push_op(RTGPU_OP_MEDIUM, current_ctx(), mat_of(o), (uint32_t)id);

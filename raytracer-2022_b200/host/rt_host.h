@@ -138,6 +138,7 @@ struct XZRect { static Obj new_(Scene &s, double x0, double x1, double z0, doubl
 struct YZRect { static Obj new_(Scene &s, double y0, double y1, double z0, double z1, double k, Mat m); }; // aarect.rs:193
 struct Boxes { static Obj new_(Scene &s, Point3 p0, Point3 p1, Mat m); };                                // boxes.rs:19
 struct Triangle { static Obj new_(Scene &s, Point3 a, Point3 b, Point3 c, Mat m); };                     // triangle.rs:22
+struct Ring { static Obj new_(Scene &s, double r, double t, Mat m); };                                    // ring.rs:22
 struct ConstantMedium {
     static Obj new_(Scene &s, Obj boundary, double d, Color c);    // constantmedium.rs:36
     static Obj new_arc(Scene &s, Obj boundary, double d, Tex a);   // constantmedium.rs:26
@@ -182,10 +183,11 @@ SceneLists random_scene(Scene &s);                            // scene.rs:22-84
 SceneLists cornell_box(Scene &s);                             // scene.rs:165-196
 SceneLists cornell_smoke(Scene &s);                           // scene.rs:199-257
 SceneLists final_scene(Scene &s, const SceneOptions &o);      // scene.rs:260-362
+SceneLists wwscene(Scene &s, const SceneOptions &o);          // scene.rs:468-571 (without get_ship: Ship.obj is missing upstream)
 void get_shuttle(Scene &s, HittableList &world, const SceneOptions &o, double zoom, double angle, Vec3 offset); // scene.rs:364-414
 /* the five BASELINE.json configs: scene function + camera + background + BvhNode::new_list
  * over the world list (main.rs:68-90).  name: "random_scene" | "cornell_box" | "final_scene" |
- * "obj_cornell" | "cornell_smoke" | "cornell_book3". */
+ * "obj_cornell" | "cornell_smoke" | "cornell_book3" | "wwscene". */
 void build_config(Scene &s, const std::string &name, double aspect_ratio, const SceneOptions &o);
 
 /* ---- lowering: graph -> flat arrays of include/rtgpu.h -------------------------------------- */

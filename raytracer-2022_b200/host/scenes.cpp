@@ -207,6 +207,71 @@ static SceneLists cornell_book3(Scene &s) {
     return out;
 }
 
+static Vec3 random_in_unit_xz_disk(Scene &s) { // basic/vec.rs:98-106
+    for (;;) {
+        double x = s.gen_range(-1.0, 1.0);
+        double z = s.gen_range(-1.0, 1.0);
+        Vec3 p(x, 0., z);
+        if (p.length() < 1.) return p;
+    }
+}
+
+// scene.rs:468-571, the scene main.rs:89 ships with.  `get_ship` is left out: source/obj/Ship.obj is
+// missing from the reference checkout (.MISSING_LARGE_BLOBS), so upstream itself cannot build it.
+// `a..=b` float ranges are drawn like `a..b` (the closed end has measure zero).
+SceneLists wwscene(Scene &s, const SceneOptions &o) {
+    SceneLists out;
+    HittableList &world = out.world;
+    // Lights
+    Mat light_strong = DiffuseLight::new_(s, Color::new_(130., 130., 130.));
+    Obj light_sphere = Sphere::new_(s, Point3::new_(800., 700., -800.), 70., light_strong);
+    world.add(light_sphere);
+    out.lights.add(Sphere::new_(s, Point3::new_(800., 700., -800.), 70., light_strong)); // `.clone()`
+    // Saturn, Jupiter, Mars
+    world.add(Sphere::new_(s, Point3::new_(0., 0., 0.), 43., Lambertian::new_arc(s, ImageTexture::new_(s, o.asset_dir + "Saturn.jpg"))));
+    world.add(Sphere::new_(s, Point3::new_(150., 20., 150.), 26., Lambertian::new_arc(s, ImageTexture::new_(s, o.asset_dir + "Jupiter.jpg"))));
+    world.add(Sphere::new_(s, Point3::new_(480., 25., 500.), 25., Lambertian::new_arc(s, ImageTexture::new_(s, o.asset_dir + "Mars.jpg"))));
+    // ring stars
+    for (int i = 0; i < 40; ++i) {
+        Vec3 pos = random_in_unit_xz_disk(s).to_unit() * (100. + s.gen_range(-15.0, 15.0));
+        pos = pos + Vec3::new_(0., 0., s.gen_range(-1.0, 1.0));
+        Color albedo = s.random_vec(0.5, 1.);
+        double fuzz = s.gen_range(0.0, 0.5);
+        double radius = s.gen_range(0.3, 0.5);
+        world.add(Sphere::new_(s, pos, radius, Metal::new_(s, albedo, fuzz)));
+    }
+    for (int i = 0; i < 40; ++i) {
+        Vec3 pos = random_in_unit_xz_disk(s).to_unit() * (100. + s.gen_range(-15.0, 15.0));
+        pos = pos + Vec3::new_(0., 0., s.gen_range(-1.0, 1.0));
+        double radius = s.gen_range(0.3, 0.6);
+        world.add(Sphere::new_(s, pos, radius, Dielectric::new_(s, 1.5)));
+    }
+    // ring
+    const int CNT = 20, delta = 2;
+    const int weight[CNT] = {2, 3, 2, 3, 4, 3, 2, 2, 3, 2, 3, 4, 3, 6, 4, 5, 3, 3, 4, 3};
+    int now = 80;
+    Mat ring_mat = Lambertian::new_(s, Color::new_(0.78, 0.78, 0.78));
+    for (int k = 0; k < CNT; ++k) {
+        for (int i = now * weight[k]; i < (now + delta) * weight[k]; ++i) {
+            double thickness = weight[k] <= 4 ? s.gen_range(0.009, 0.01) : s.gen_range(0.007, 0.008);
+            world.add(Ring::new_(s, (double)i / (double)weight[k], thickness, ring_mat));
+        }
+        now += delta;
+    }
+    // star
+    for (int i = 0; i <= 100; ++i) {
+        Color scolor = (i % 2 == 0) ? Color::new_(1., 1., 1.) : Color::new_(1., 1., 0.);
+        double x = s.gen_range(-500.0, 500.0);
+        double y = s.gen_range(-500.0, 500.0);
+        double z = s.gen_range(100.0, 400.0);
+        double radius = s.gen_range(0.3, 0.45);
+        world.add(Sphere::new_(s, Point3::new_(x, y, z), radius, DiffuseLight::new_(s, scolor)));
+    }
+    // Import Object
+    get_shuttle(s, world, o, 13.5, 56., Vec3::new_(40.88, 1.3, -85.59));
+    return out;
+}
+
 void build_config(Scene &s, const std::string &name, double aspect_ratio, const SceneOptions &o) {
     SceneLists l;
     Vec3 vup = Vec3::new_(0., 1., 0.);
@@ -220,6 +285,9 @@ void build_config(Scene &s, const std::string &name, double aspect_ratio, const 
     } else if (name == "final_scene") { // C3 / C5
         l = final_scene(s, o);
         s.set_camera(Point3::new_(478., 278., -600.), Point3::new_(278., 278., 0.), vup, 40., aspect_ratio, 0., 10., 0., 1.);
+    } else if (name == "wwscene") { // the shipped default: main.rs:43-51 camera
+        l = wwscene(s, o);
+        s.set_camera(Point3::new_(0., 15., -150.), Point3::new_(35., 0., 0.), Vec3::new_(1., 5., 0.), 40., aspect_ratio, 0.0, 10., 0., 1.);
     } else if (name == "obj_cornell") { // C4
         l = obj_cornell(s, o);
         s.set_camera(Point3::new_(278., 278., -800.), Point3::new_(278., 278., 0.), vup, 40., aspect_ratio, 0., 10., 0., 1.);

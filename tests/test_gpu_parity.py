@@ -13,7 +13,7 @@ from oracle_lib import OracleScene, make_rays
 pytestmark = pytest.mark.gpu
 
 F64_MAX = np.finfo(np.float64).max
-CONFIGS = ["random_scene", "cornell_box", "final_scene", "obj_cornell", "cornell_smoke", "cornell_book3"]
+CONFIGS = ["random_scene", "cornell_box", "final_scene", "obj_cornell", "cornell_smoke", "cornell_book3", "wwscene"]
 _cache = {}
 
 
@@ -73,6 +73,8 @@ def test_trace_batch_config_scenes(name):
     lo, hi = box[:3], box[3:]
     if name == "final_scene":
         lo, hi = np.array([-1000.0, 0, -1000]), np.array([1000.0, 600, 1000])
+    if name == "wwscene":
+        lo, hi = np.array([-150.0, -30, -150]), np.array([200.0, 60, 200])
     batches.append(random_rays(rng, 1 << 14, lo, hi))
     rays = np.concatenate(batches)
     keys = np.arange(rays.shape[0], dtype=np.uint64) * 7919 + 13
@@ -194,7 +196,7 @@ def test_constant_medium_draws_match():
     compare_hits(g, o)
 
 
-@pytest.mark.parametrize("name", ["cornell_box", "random_scene", "final_scene", "cornell_book3", "cornell_smoke", "obj_cornell"])
+@pytest.mark.parametrize("name", ["cornell_box", "random_scene", "final_scene", "cornell_book3", "cornell_smoke", "obj_cornell", "wwscene"])
 def test_per_sample_radiance(name):
     """Same Philox slots, same control flow: one-sample radiance agrees path by path.  Paths
     whose direction passes through GPU sin/cos/acos (1-ulp differences) can diverge after many

@@ -149,6 +149,18 @@ def test_jpeg_decoder_against_libjpeg():
     assert diff.max() <= 3 and diff.mean() < 0.3, (diff.max(), diff.mean())
 
 
+@pytest.mark.parametrize("name", ["Saturn.jpg", "Jupiter.jpg", "Mars.jpg"])
+def test_jpeg_decoder_420_against_libjpeg(name):
+    """the planet textures of wwscene are 4:2:0: chroma goes through the h2v2 triangle upsampler"""
+    from PIL import Image
+    path = os.path.join(rt.ASSET_DIR, name)
+    mine = rt.decode_jpeg(path)
+    ref = np.asarray(Image.open(path).convert("RGB"))
+    assert mine.shape == ref.shape
+    diff = np.abs(mine.astype(int) - ref.astype(int))
+    assert diff.max() <= 6 and diff.mean() < 0.6, (diff.max(), diff.mean())
+
+
 def test_image_texture_rows_are_stored_bottom_up():
     s = rt.Scene(seed=1)
     img = np.zeros((2, 2, 3), dtype=np.uint8)
@@ -165,7 +177,7 @@ def test_image_texture_rows_are_stored_bottom_up():
 
 def test_config_scenes_build_and_lower():
     for name, nobj in (("random_scene", 400), ("cornell_box", 6), ("final_scene", 1400), ("obj_cornell", 13079),
-                       ("cornell_smoke", 8), ("cornell_book3", 8)):
+                       ("cornell_smoke", 8), ("cornell_book3", 8), ("wwscene", 13079 + 128 + 185)):
         s = rt.Scene(seed=2022).build_config(name)
         g = s.graph()
         assert g.n_objects >= nobj and g.world >= 0

@@ -180,6 +180,17 @@ def test_k12_constant_medium():
     assert abs(frac - (1 - math.exp(-140 / 5))) < 1e-9 or frac > 0.99
 
 
+def test_ring_known_answers():
+    """Ring(r=10, t=1): annulus 9..11 in the plane y = 0 (ring.rs:22-52)"""
+    s, o = one_object_scene(lambda s: s.ring(10.0, 1.0, s.lambertian((0.78, 0.78, 0.78))))
+    h = o.trace_batch(make_rays([(10, 5, 0), (8.5, 5, 0), (9, 5, 0), (0, -2, 10.5), (10, 5, 0)],
+                                [(0, -1, 0), (0, -1, 0), (0, -1, 0), (0, 1, 0), (1, 0, 0)]))
+    assert h["hit"].tolist() == [1, 0, 1, 1, 0]  # inside, too close, on the inner edge (inclusive), from below, parallel
+    assert h["t"][0] == 5.0 and np.array_equal(h["n"][0], [0, 1, 0]) and h["front_face"][0] == 1
+    assert h["t"][3] == 2.0 and np.array_equal(h["n"][3], [0, -1, 0]) and h["front_face"][3] == 0
+    assert np.allclose(s.bounding_box(s.graph().world), [-11, -0.0001, -11, 11, 0.0001, 11])
+
+
 def test_philox_known_answers():
     # Random123 kat_vectors: philox4x32-10
     assert philox([0, 0, 0, 0], [0, 0]).tolist() == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]

@@ -3,13 +3,14 @@ import sys
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import rtb200 as rt
 
-cfgs = {"final_scene": (800, 800, 8), "random_scene": (400, 225, 64), "cornell_box": (600, 600, 16), "obj_cornell": (600, 600, 8)}
+cfgs = {"final_scene": (800, 800, 8), "random_scene": (400, 225, 64), "cornell_box": (600, 600, 16), "obj_cornell": (600, 600, 8), "wwscene": (1280, 720, 8),
+        "cornell_smoke": (600, 600, 16), "cornell_book3": (600, 600, 16)}
 names = sys.argv[1:] or ["final_scene"]
 for name in names:
     w, h, spp = cfgs[name]
     s = rt.Scene(seed=2022).build_config(name, w / h)
     gpu = rt.GpuScene(s.lower(), 0)
-    gpu.render(w, h, 0, 2)
+    gpu.render(w, h, 0, spp)  # also sizes the wave buffers
     best = None
     for rep in range(3):
         acc, st = gpu.render(w, h, 0, spp)
