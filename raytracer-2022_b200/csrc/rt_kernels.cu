@@ -45,12 +45,48 @@ constexpr int kThreads = 128;
 constexpr int kSMs = 148;
 constexpr int kBlocksPerSM = 8;
 
-struct PathQueue { /* SoA, one slot per live path */
-    double *ox, *oy, *oz, *dx, *dy, *dz, *tm; /* ray */
-    double *bx, *by, *bz;                      /* throughput */
-    uint32_t *pid;                             /* path id inside the wave */
-    uint32_t *rng;                             /* next slot of the path's Philox stream */
+/* One queue entry = a 64-byte ray record + a 32-byte state record (AoS): k_extend reads the ray record of
+ * consecutive entries with four 128-bit loads (fully coalesced), and the shade kernels, which reach entries
+ * through the per-class index lists, touch 3 sectors per path instead of the 12 an SoA layout costs. */
+struct __align__(16) RayRec {
+    double ox, oy, oz, dx, dy, dz, tm;
+    uint32_t pid; /* path id inside the wave */
+    uint32_t rng; /* next slot of the path's Philox stream */
 };
+struct __align__(16) StateRec {
+    double bx, by, bz, pad_; /* throughput */
+};
+static_assert(sizeof(RayRec) == 64 && sizeof(StateRec) == 32, "queue records");
+struct PathQueue {
+    RayRec *ray;
+    StateRec *st;
+};
+__device__ __forceinline__ RayRec ld_ray(const RayRec *p) {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    double2 a = q[0], b = q[1], c = q[2], d = q[3];
+    RayRec r;
+    r.ox = a.x; r.oy = a.y; r.oz = b.x; r.dx = b.y; r.dy = c.x; r.dz = c.y; r.tm = d.x;
+    r.pid = (uint32_t)__double2loint(d.y);
+    r.rng = (uint32_t)__double2hiint(d.y);
+    return r;
+}
+__device__ __forceinline__ void st_ray(RayRec *p, V3 o, V3 d, double tm, uint32_t pid, uint32_t rng) {
+    double2 *q = reinterpret_cast<double2 *>(p);
+    q[0] = make_double2(o.x, o.y);
+    q[1] = make_double2(o.z, d.x);
+    q[2] = make_double2(d.y, d.z);
+    q[3] = make_double2(tm, __hiloint2double((int)rng, (int)pid));
+}
+__device__ __forceinline__ V3 ld_beta(const StateRec *p) {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    double2 a = q[0], b = q[1];
+    return v3(a.x, a.y, b.x);
+}
+__device__ __forceinline__ void st_beta(StateRec *p, V3 b) {
+    double2 *q = reinterpret_cast<double2 *>(p);
+    q[0] = make_double2(b.x, b.y);
+    q[1] = make_double2(b.z, 0.);
+}
 struct HitBuf {
     double *t;
     uint32_t *op; /* op index | box face << 29; RT_NO_HIT = miss */
@@ -94,12 +130,8 @@ __global__ void __launch_bounds__(kThreads) k_raygen(DScene sc, PathQueue q, Wav
         rt_rng rng;
         path_rng(rng, wp, pid, 0);
         Ray r = camera_ray(sc.cam, (int)(pixel % (uint32_t)wp.width), (int)(pixel / (uint32_t)wp.width), wp.width, wp.height, rng);
-        q.ox[pid] = r.o.x; q.oy[pid] = r.o.y; q.oz[pid] = r.o.z;
-        q.dx[pid] = r.d.x; q.dy[pid] = r.d.y; q.dz[pid] = r.d.z;
-        q.tm[pid] = r.tm;
-        q.bx[pid] = 1.; q.by[pid] = 1.; q.bz[pid] = 1.;
-        q.pid[pid] = pid;
-        q.rng[pid] = rng.pos;
+        st_ray(q.ray + pid, r.o, r.d, r.tm, pid, rng.pos);
+        st_beta(q.st + pid, v3(1., 1., 1.));
     }
 }
 
@@ -113,13 +145,14 @@ struct QueueIO {
     WaveParams wp;
     uint32_t pid, pos, cur;
     __device__ __forceinline__ void load(uint32_t idx, V3 &o, V3 &d, double &tm, double &tmin, double &tmax) {
-        o = v3(q.ox[idx], q.oy[idx], q.oz[idx]);
-        d = v3(q.dx[idx], q.dy[idx], q.dz[idx]);
-        tm = q.tm[idx];
+        RayRec rr = ld_ray(q.ray + idx);
+        o = v3(rr.ox, rr.oy, rr.oz);
+        d = v3(rr.dx, rr.dy, rr.dz);
+        tm = rr.tm;
         tmin = 0.001;
         tmax = RT_F64_MAX;
-        pid = q.pid[idx];
-        pos = q.rng[idx];
+        pid = rr.pid;
+        pos = rr.rng;
         cur = idx;
     }
     __device__ __forceinline__ double draw() { /* the path's stream resumes at slot `pos` */
@@ -132,7 +165,7 @@ struct QueueIO {
     __device__ __forceinline__ void store(uint32_t idx, const Closest &c) {
         hb.t[idx] = c.t;
         hb.op[idx] = c.op == RT_NO_HIT ? RT_NO_HIT : (c.op | (c.face << 29));
-        q.rng[idx] = pos;
+        q.ray[idx].rng = pos;
     }
 };
 __global__ void __launch_bounds__(kThreads, RT_EXTEND_MIN_BLOCKS) k_extend(DScene sc, PathQueue q, HitBuf hb, const uint32_t *count,
@@ -273,13 +306,14 @@ __global__ void __launch_bounds__(kThreads) k_shade(DScene sc, PathQueue qin, Hi
         if (j < n) {
             uint32_t i = class_idx[j];
             Ray r;
-            r.o = v3(qin.ox[i], qin.oy[i], qin.oz[i]);
-            r.d = v3(qin.dx[i], qin.dy[i], qin.dz[i]);
-            r.tm = qin.tm[i];
-            beta = v3(qin.bx[i], qin.by[i], qin.bz[i]);
-            pid = qin.pid[i];
+            RayRec rr = ld_ray(qin.ray + i);
+            r.o = v3(rr.ox, rr.oy, rr.oz);
+            r.d = v3(rr.dx, rr.dy, rr.dz);
+            r.tm = rr.tm;
+            beta = ld_beta(qin.st + i);
+            pid = rr.pid;
             rt_rng rng;
-            path_rng(rng, wp, pid, qin.rng[i]);
+            path_rng(rng, wp, pid, rr.rng);
             V3 contrib;
             alive = shade_segment<CLS>(sc, r, hb.t[i], hb.op[i], rng, beta, next, contrib);
             pos = rng.pos;
@@ -301,12 +335,8 @@ __global__ void __launch_bounds__(kThreads) k_shade(DScene sc, PathQueue qin, Hi
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (alive) {
                     uint32_t k = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
-                    qout.ox[k] = next.o.x; qout.oy[k] = next.o.y; qout.oz[k] = next.o.z;
-                    qout.dx[k] = next.d.x; qout.dy[k] = next.d.y; qout.dz[k] = next.d.z;
-                    qout.tm[k] = next.tm;
-                    qout.bx[k] = beta.x; qout.by[k] = beta.y; qout.bz[k] = beta.z;
-                    qout.pid[k] = pid;
-                    qout.rng[k] = pos;
+                    st_ray(qout.ray + k, next.o, next.d, next.tm, pid, pos);
+                    st_beta(qout.st + k, beta);
                 }
             }
         }
@@ -329,7 +359,7 @@ __global__ void k_sort_bounds(PathQueue q, const uint32_t *count, double *moment
     double s1[3] = {0., 0., 0.}, s2[3] = {0., 0., 0.}, cnt = 0.;
     uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride * 4) { /* every 4th stripe: a sample is enough */
-        double x = q.ox[i], y = q.oy[i], z = q.oz[i];
+        double x = q.ray[i].ox, y = q.ray[i].oy, z = q.ray[i].oz;
         if (fabs(x) < 1e30 && fabs(y) < 1e30 && fabs(z) < 1e30) {
             s1[0] += x; s1[1] += y; s1[2] += z;
             s2[0] += x * x; s2[1] += y * y; s2[2] += z * z;
@@ -373,8 +403,9 @@ __global__ void k_sort_keys(PathQueue q, const uint32_t *count, const double *mo
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
         uint32_t key = 0xffffffffu;
         if (i < n) {
-            float o[3] = {(float)q.ox[i], (float)q.oy[i], (float)q.oz[i]};
-            float d[3] = {(float)q.dx[i], (float)q.dy[i], (float)q.dz[i]};
+            RayRec rr = ld_ray(q.ray + i);
+            float o[3] = {(float)rr.ox, (float)rr.oy, (float)rr.oz};
+            float d[3] = {(float)rr.dx, (float)rr.dy, (float)rr.dz};
             uint32_t cell[3];
             for (int c = 0; c < 3; ++c) {
                 float t = (o[c] - lo[c]) * inv[c];
@@ -400,12 +431,12 @@ __global__ void k_sort_gather(PathQueue src, PathQueue dst, const uint32_t *coun
     uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
         uint32_t i = idx[j];
-        dst.ox[j] = src.ox[i]; dst.oy[j] = src.oy[i]; dst.oz[j] = src.oz[i];
-        dst.dx[j] = src.dx[i]; dst.dy[j] = src.dy[i]; dst.dz[j] = src.dz[i];
-        dst.tm[j] = src.tm[i];
-        dst.bx[j] = src.bx[i]; dst.by[j] = src.by[i]; dst.bz[j] = src.bz[i];
-        dst.pid[j] = src.pid[i];
-        dst.rng[j] = src.rng[i];
+        const uint4 *a = reinterpret_cast<const uint4 *>(src.ray + i);
+        uint4 *b = reinterpret_cast<uint4 *>(dst.ray + j);
+        b[0] = a[0]; b[1] = a[1]; b[2] = a[2]; b[3] = a[3];
+        const uint4 *c = reinterpret_cast<const uint4 *>(src.st + i);
+        uint4 *e = reinterpret_cast<uint4 *>(dst.st + j);
+        e[0] = c[0]; e[1] = c[1];
     }
 }
 
@@ -708,20 +739,21 @@ rtgpu_status ensure_wave(rtgpu_scene *s, size_t n_paths, int max_depth) {
     s->wave_mem = nullptr;
     s->cap = 0;
     size_t n = (n_paths + 255) & ~(size_t)255;
-    /* per path: 2 queues x (10 doubles + 2 u32) + hit (double + u32) + contrib (3 doubles) + path_len */
-    size_t bytes = n * (2 * (10 * 8 + 2 * 4) + 8 + 4 + 3 * 8 + 4 + 4 * 4 + kClasses * 4) + 256;
+    /* per path: 2 queues x (64 B ray + 32 B state) + hit (double + u32) + contrib (3 doubles) + path_len + sort/class lists */
+    size_t bytes = n * (2 * (sizeof(RayRec) + sizeof(StateRec)) + 8 + 4 + 3 * 8 + 4 + 4 * 4 + kClasses * 4) + 256;
     CK(cudaMalloc(&s->wave_mem, bytes));
     char *p = static_cast<char *>(s->wave_mem);
     auto take_d = [&](double *&dst) { dst = reinterpret_cast<double *>(p); p += n * 8; };
     auto take_u = [&](uint32_t *&dst) { dst = reinterpret_cast<uint32_t *>(p); p += n * 4; };
     for (int k = 0; k < 2; ++k) {
         PathQueue &q = s->q[k];
-        take_d(q.ox); take_d(q.oy); take_d(q.oz); take_d(q.dx); take_d(q.dy); take_d(q.dz); take_d(q.tm);
-        take_d(q.bx); take_d(q.by); take_d(q.bz);
+        q.ray = reinterpret_cast<RayRec *>(p);
+        p += n * sizeof(RayRec);
+        q.st = reinterpret_cast<StateRec *>(p);
+        p += n * sizeof(StateRec);
     }
     take_d(s->hb.t);
     take_d(s->cx); take_d(s->cy); take_d(s->cz);
-    for (int k = 0; k < 2; ++k) { take_u(s->q[k].pid); take_u(s->q[k].rng); }
     take_u(s->hb.op);
     take_u(s->path_len);
     s->class_idx = reinterpret_cast<uint32_t *>(p);
