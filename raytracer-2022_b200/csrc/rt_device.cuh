@@ -64,9 +64,6 @@ struct DScene {
 };
 
 /* ---- 128-bit loads of an op ------------------------------------------------------------- */
-struct OpData {
-    double d[6];
-};
 __device__ __forceinline__ uint4 load_op_header(const rtgpu_op *op) { return __ldg(reinterpret_cast<const uint4 *>(op)); }
 __device__ __forceinline__ void load_op_payload(const rtgpu_op *op, double d[6]) {
     const double2 *p = reinterpret_cast<const double2 *>(op) + 1;
