@@ -1,0 +1,182 @@
+/*
+ * rt_render.cpp -- native driver: what `cargo run --release` does upstream (raytracer/src/main.rs:28-231),
+ * with the hot path on B200s.
+ *
+ *   [1/5] consts -> camera            main.rs:33-78     (command line instead of editing consts)
+ *   [2/5] scene + BvhNode::new_list   main.rs:89-90     rt::build_config (host/scenes.cpp), rt::lower
+ *         render                      main.rs:93-163    rtgpu_render, one host thread per GPU, spp-sharded
+ *   [3/5] collect                     main.rs:171-183   ONE ncclReduce(sum) of the float accumulation buffers
+ *   [4/5] write_color + row flip      main.rs:191-201   rtgpu_resolve
+ *   [5/5] image file                  main.rs:213-221   binary PPM (the JPEG encoder is out of scope)
+ *
+ * Build: see __graft_entry__.build().  Links librthost.so, librtgpu.so and the system libnccl.
+ */
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../host/rt_host.h"
+
+namespace {
+
+struct Args {
+    std::string scene = "final_scene", out = "output.ppm", assets = "assets/";
+    int width = 800, height = 800, spp = 100, depth = 50, devices = 1;
+    uint64_t seed = 2022;
+};
+
+bool parse(int argc, char **argv, Args &a) {
+    for (int i = 1; i < argc; ++i) {
+        std::string k = argv[i];
+        auto val = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
+        if (k == "--scene") a.scene = val();
+        else if (k == "--out") a.out = val();
+        else if (k == "--assets") a.assets = val();
+        else if (k == "--width") a.width = atoi(val());
+        else if (k == "--height") a.height = atoi(val());
+        else if (k == "--spp") a.spp = atoi(val());
+        else if (k == "--depth") a.depth = atoi(val());
+        else if (k == "--devices") a.devices = atoi(val());
+        else if (k == "--seed") a.seed = strtoull(val(), nullptr, 10);
+        else {
+            fprintf(stderr,
+                    "usage: rt_render [--scene random_scene|cornell_box|cornell_smoke|cornell_book3|final_scene|obj_cornell|wwscene]\n"
+                    "                 [--width W --height H --spp N --depth D --seed S --devices G --assets DIR --out FILE.ppm]\n");
+            return false;
+        }
+    }
+    if (!a.assets.empty() && a.assets.back() != '/') a.assets += '/';
+    return a.width >= 2 && a.height >= 2 && a.spp >= 1 && a.devices >= 1;
+}
+
+} // namespace
+
+int main(int argc, char **argv) {
+    Args a;
+    if (!parse(argc, argv, a)) return 2;
+    auto t_begin = std::chrono::steady_clock::now();
+    printf("[1/5] Initializing...\nIMAGE SIZE: %dx%d\nSAMPLE PER PIXEL: %d\nMAX DEPTH: %d\nSCENE: %s (seed %llu)\n", a.width, a.height,
+           a.spp, a.depth, a.scene.c_str(), (unsigned long long)a.seed);
+    int have = rtgpu_device_count();
+    if (have < 1) {
+        fprintf(stderr, "no CUDA device: the hot path has no CPU fallback\n");
+        return 1;
+    }
+    if (a.devices > have) a.devices = have;
+    if (a.devices > a.spp) a.devices = a.spp;
+
+    // ---- scene: the reference's constructors, BvhNode::new_list, then lowering ----
+    rt::Lowered lowered;
+    try {
+        rt::Scene scene(a.seed);
+        rt::SceneOptions opt;
+        opt.asset_dir = a.assets;
+        rt::build_config(scene, a.scene, (double)a.width / (double)a.height, opt);
+        rt_graph g = scene.view();
+        lowered = rt::lower(g);
+        printf("[2/5] Rendering with %d GPU(s)... (%d objects -> %zu ops, %.1f KB)\n", a.devices, g.n_objects, lowered.ops.size(),
+               lowered.ops.size() * 64 / 1024.0);
+    } catch (const rt::Error &e) {
+        fprintf(stderr, "scene error: %s\n", e.what.c_str());
+        return 1;
+    }
+    rtgpu_scene_desc desc = lowered.desc();
+    const size_t n_float = (size_t)3 * a.width * a.height;
+
+    // ---- render: GPU g takes sample indices [g*spp/G, (g+1)*spp/G) of every pixel ----
+    std::vector<ncclComm_t> comms((size_t)a.devices);
+    std::vector<int> devs((size_t)a.devices);
+    for (int g = 0; g < a.devices; ++g) devs[g] = g;
+    if (a.devices > 1 && ncclCommInitAll(comms.data(), a.devices, devs.data()) != ncclSuccess) {
+        fprintf(stderr, "ncclCommInitAll failed\n");
+        return 1;
+    }
+    std::vector<float *> accum((size_t)a.devices, nullptr);
+    std::vector<rtgpu_stats> stats((size_t)a.devices);
+    std::vector<int> status((size_t)a.devices, 0);
+    auto t_render = std::chrono::steady_clock::now();
+    std::vector<std::thread> pool;
+    for (int g = 0; g < a.devices; ++g)
+        pool.emplace_back([&, g]() {
+            cudaSetDevice(g);
+            rtgpu_scene *sc = nullptr;
+            if (rtgpu_scene_create(&desc, g, &sc) != RTGPU_OK || cudaMalloc(&accum[g], n_float * sizeof(float)) != cudaSuccess) {
+                fprintf(stderr, "GPU %d: %s\n", g, rtgpu_last_error());
+                status[g] = 1;
+                return;
+            }
+            rtgpu_render_params p;
+            memset(&p, 0, sizeof p);
+            p.width = a.width;
+            p.height = a.height;
+            p.spp_begin = (int)((long long)g * a.spp / a.devices);
+            p.spp_end = (int)((long long)(g + 1) * a.spp / a.devices);
+            p.max_depth = a.depth;
+            p.device = g;
+            p.seed = a.seed;
+            p.accum_on_device = 1;
+            if (rtgpu_render(sc, &p, accum[g], &stats[g]) != RTGPU_OK) {
+                fprintf(stderr, "GPU %d: %s\n", g, rtgpu_last_error());
+                status[g] = 1;
+            }
+            rtgpu_scene_destroy(sc);
+        });
+    for (auto &t : pool) t.join();
+    for (int g = 0; g < a.devices; ++g)
+        if (status[g]) return 1;
+
+    // ---- collect: one sum-reduce of the per-GPU radiance sums to GPU 0 ----
+    printf("[3/5] Collecting results...\n");
+    if (a.devices > 1) {
+        ncclGroupStart();
+        for (int g = 0; g < a.devices; ++g) {
+            cudaSetDevice(g);
+            ncclReduce(accum[g], accum[g], n_float, ncclFloat, ncclSum, 0, comms[g], 0);
+        }
+        ncclGroupEnd();
+        for (int g = 0; g < a.devices; ++g) {
+            cudaSetDevice(g);
+            cudaStreamSynchronize(0);
+        }
+    }
+    double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_render).count();
+    uint64_t rays = 0, samples = 0;
+    for (int g = 0; g < a.devices; ++g) {
+        rays += stats[g].rays;
+        samples += stats[g].samples;
+    }
+    printf("      %.3f s, %.1f Mrays/s, %.1f Msamples/s, %.2f rays/sample\n", sec, rays / sec / 1e6, samples / sec / 1e6,
+           (double)rays / (double)(samples ? samples : 1));
+
+    // ---- image ----
+    printf("[4/5] Generating image...\n");
+    std::vector<uint8_t> rgb((size_t)3 * a.width * a.height);
+    cudaSetDevice(0);
+    if (rtgpu_resolve(accum[0], a.width, a.height, a.spp, 1, rgb.data()) != RTGPU_OK) {
+        fprintf(stderr, "resolve: %s\n", rtgpu_last_error());
+        return 1;
+    }
+    printf("[5/5] Output image as \"%s\"\n", a.out.c_str());
+    FILE *f = fopen(a.out.c_str(), "wb");
+    if (!f) {
+        fprintf(stderr, "Outputting image fails.\n");
+        return 1;
+    }
+    fprintf(f, "P6\n%d %d\n255\n", a.width, a.height);
+    fwrite(rgb.data(), 1, rgb.size(), f);
+    fclose(f);
+    for (int g = 0; g < a.devices; ++g) {
+        cudaSetDevice(g);
+        cudaFree(accum[g]);
+        if (a.devices > 1) ncclCommDestroy(comms[g]);
+    }
+    printf("\n      All Work Done.\n      Elapsed Time: %.2f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count());
+    return 0;
+}
