@@ -41,7 +41,17 @@ thread_local std::string g_err;
         }                                                                                                          \
     } while (0)
 
-constexpr int kThreads = 128;
+#ifndef RT_THREADS
+#define RT_THREADS 128
+#endif
+constexpr int kThreads = RT_THREADS;
+#ifndef RT_SHADE_THREADS
+#define RT_SHADE_THREADS 64
+#endif
+#ifndef RT_SHADE_BLOCKS_PER_SM
+#define RT_SHADE_BLOCKS_PER_SM 8 /* 16 warps/SM: measured best (5 % over 32 warps/SM) */
+#endif
+constexpr int kShadeThreads = RT_SHADE_THREADS;
 constexpr int kSMs = 148;
 constexpr int kBlocksPerSM = 8;
 
@@ -291,7 +301,7 @@ __device__ __forceinline__ bool shade_segment(const DScene &sc, const Ray &r, do
 }
 
 template <int CLS>
-__global__ void __launch_bounds__(kThreads) k_shade(DScene sc, PathQueue qin, HitBuf hb, PathQueue qout, const uint32_t *class_count,
+__global__ void __launch_bounds__(kShadeThreads) k_shade(DScene sc, PathQueue qin, HitBuf hb, PathQueue qout, const uint32_t *class_count,
                                                     const uint32_t *class_idx, uint32_t *count_out, double *cx, double *cy, double *cz,
                                                     uint32_t *path_len, WaveParams wp, uint32_t bounce) {
     uint32_t n = class_count[CLS];
@@ -841,7 +851,7 @@ rtgpu_status run_wave(rtgpu_scene *s, const WaveParams &wp, int max_depth, cudaS
             uint32_t *pl = want_len ? s->path_len : nullptr;
             uint32_t cap = (uint32_t)s->cap;
             k_classify<<<blocks, 256, 0, stream>>>(s->d, s->mat_class, s->hb, s->counts + b, cc, s->class_idx, cap);
-#define RT_SHADE(C) k_shade<C><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, qout, cc, s->class_idx + (size_t)C * cap, s->counts + b + 1, \
+#define RT_SHADE(C) k_shade<C><<<kSMs * RT_SHADE_BLOCKS_PER_SM, kShadeThreads, 0, stream>>>(s->d, qin, s->hb, qout, cc, s->class_idx + (size_t)C * cap, s->counts + b + 1, \
                                                                 s->cx, s->cy, s->cz, pl, wp, (uint32_t)b)
             int n_launched = 0;
             RT_SHADE(0);
