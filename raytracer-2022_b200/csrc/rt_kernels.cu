@@ -53,7 +53,10 @@ constexpr int kThreads = RT_THREADS;
 #endif
 constexpr int kShadeThreads = RT_SHADE_THREADS;
 constexpr int kSMs = 148;
-constexpr int kBlocksPerSM = 8;
+#ifndef RT_BLOCKS_PER_SM
+#define RT_BLOCKS_PER_SM 8
+#endif
+constexpr int kBlocksPerSM = RT_BLOCKS_PER_SM;
 
 /* One queue entry = a 64-byte ray record + a 32-byte state record (AoS): k_extend reads the ray record of
  * consecutive entries with four 128-bit loads (fully coalesced), and the shade kernels, which reach entries

@@ -294,3 +294,91 @@ def test_c5_resolution_smoke():
     crop_g, crop_o = a[500:532, 1000:1064].astype(np.float64), ref[500:532, 1000:1064]
     close = np.abs(crop_g - crop_o).max(axis=2) <= 1e-5 * np.maximum(1.0, np.abs(crop_o).max(axis=2))
     assert close.mean() > 0.97
+
+
+def _fuzz_scene(seed):
+    """random object graph: every primitive kind, random wrapper chains (nested up to 3 PUSH levels),
+    lists, BVHs over mixed content, media over spheres / boxes / instances"""
+    rng = np.random.default_rng(seed)
+    s = rt.Scene(seed=1000 + seed)
+    mats = [s.lambertian(tuple(rng.uniform(0, 1, 3))), s.metal(tuple(rng.uniform(0.5, 1, 3)), float(rng.uniform(0, 0.5))),
+            s.dielectric(1.5), s.diffuse_light((4, 4, 4)), s.lambertian(s.checker_texture((0.2, 0.3, 0.1), (0.9, 0.9, 0.9)))]
+
+    def prim():
+        k = int(rng.integers(0, 8))
+        m = mats[int(rng.integers(0, len(mats)))]
+        c = rng.uniform(-4, 4, 3)
+        if k == 0:
+            return s.sphere(c, float(rng.uniform(0.2, 1.5)), m)
+        if k == 1:
+            return s.moving_sphere(c, c + rng.uniform(-0.5, 0.5, 3), 0.0, 1.0, float(rng.uniform(0.2, 1.0)), m)
+        if k in (2, 3, 4):
+            a0, b0 = rng.uniform(-4, 2, 2)
+            f = (s.xy_rect, s.xz_rect, s.yz_rect)[k - 2]
+            return f(a0, a0 + float(rng.uniform(0.5, 3)), b0, b0 + float(rng.uniform(0.5, 3)), float(rng.uniform(-4, 4)), m)
+        if k == 5:
+            return s.boxes(c, c + rng.uniform(0.3, 2.5, 3), m)
+        if k == 6:
+            return s.triangle(c, c + rng.uniform(-2, 2, 3), c + rng.uniform(-2, 2, 3), m)
+        return s.ring(float(rng.uniform(1, 4)), float(rng.uniform(0.1, 0.8)), m)
+
+    def wrap(o, depth):
+        for _ in range(int(rng.integers(0, 4))):
+            k = int(rng.integers(0, 4))
+            if k == 0:
+                o = s.translate(o, rng.uniform(-2, 2, 3))
+            elif k == 1:
+                o = s.rotate_y(o, float(rng.uniform(-90, 90)))
+            elif k == 2:
+                o = s.zoom(o, float(rng.uniform(0.5, 2.0)))
+            else:
+                o = s.flip_face(o)
+        return o
+
+    def node(depth):
+        k = int(rng.integers(0, 6)) if depth < 3 else 0
+        if k <= 1:
+            return wrap(prim(), depth)
+        if k == 2:
+            return wrap(s.bvh_node([node(depth + 1) for _ in range(int(rng.integers(1, 7)))]), depth)
+        if k == 3:
+            return wrap(s.hittable_list([node(depth + 1) for _ in range(int(rng.integers(1, 4)))]), depth)
+        if k == 4:  # medium over a sphere, a box or an instance of them
+            b = s.sphere(rng.uniform(-3, 3, 3), float(rng.uniform(0.5, 2.5)), mats[2]) if rng.random() < 0.5 else \
+                s.boxes(rng.uniform(-3, 0, 3), rng.uniform(0.5, 3, 3), mats[0])
+            if rng.random() < 0.5:
+                b = s.translate(s.rotate_y(b, float(rng.uniform(-45, 45))), rng.uniform(-1, 1, 3))
+            return wrap(s.constant_medium(b, float(rng.uniform(0.05, 1.0)), tuple(rng.uniform(0, 1, 3))), depth)
+        return wrap(s.bvh_node([wrap(prim(), depth) for _ in range(int(rng.integers(2, 30)))]), depth)
+
+    s.set_world(s.bvh_node([node(0) for _ in range(int(rng.integers(2, 9)))]))
+    return s
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_random_graphs(seed):
+    s = _fuzz_scene(seed)
+    try:
+        lowered = s.lower()
+    except rt.RtError as e:  # e.g. a wrapper chain longer than RT_MAX_CHAIN is refused, not mis-rendered
+        pytest.skip(str(e))
+    if lowered.desc.max_push_depth > 4:
+        with pytest.raises(rt.RtError):
+            rt.GpuScene(lowered, device=0)
+        return
+    try:
+        gpu = rt.GpuScene(lowered, device=0)
+    except rt.RtError as e:
+        assert "RT_MAX" in str(e)
+        return
+    orc = OracleScene(s)
+    rng = np.random.default_rng(100 + seed)
+    rays = random_rays(rng, 1 << 13, np.array([-7.0, -7, -7]), np.array([7.0, 7, 7]))
+    keys = rng.integers(0, 2**63, rays.shape[0], dtype=np.uint64)
+    g, _ = gpu.trace_batch(rays, keys)
+    o = orc.trace_batch(rays, keys)
+    compare_hits(g, o)
+    # with and without singleton elision the program answers the same
+    g2, _ = rt.GpuScene(s.lower(elide_singletons=False), device=0).trace_batch(rays, keys)
+    for f in ("hit", "gid", "face", "inst", "rng_pos"):
+        assert np.array_equal(g[f], g2[f])
