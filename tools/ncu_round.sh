@@ -7,4 +7,4 @@ timeout 300 $PROF > gpurun_out/plain2.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_extend -s 51 -c 2 -o gpurun_out/prof_extend -f $PROF > gpurun_out/ncu_full.log 2>&1
 timeout 300 $PROF > gpurun_out/plain3.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_shade<1>" -s 51 -c 1 -o gpurun_out/prof_shade1 -f $PROF > gpurun_out/ncu_shade1.log 2>&1
-tail -2 gpurun_out/ncu_full.log gpurun_out/ncu_shade1.log
+tail -n 2 gpurun_out/ncu_full.log
