@@ -198,3 +198,13 @@ def test_oracle_image_statistics_are_stable_across_seeds():
     b, _ = orc.render(24, 24, 64, 128, threads=4)
     ma, mb = a.mean() / 64, b.mean() / 64
     assert abs(ma - mb) / ma < 0.1
+
+
+def test_native_driver_is_built_and_parses_arguments():
+    """raytracer-2022_b200/rt_render: the reference's main.rs flow over the two libraries (needs a GPU to render)"""
+    import subprocess
+    exe = os.path.join(ROOT, "raytracer-2022_b200", "rt_render")
+    if not os.path.exists(exe):
+        pytest.skip("driver not built (no nccl.h on this machine)")
+    r = subprocess.run([exe, "--bogus"], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage: rt_render" in r.stderr
