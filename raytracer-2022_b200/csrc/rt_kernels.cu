@@ -991,6 +991,12 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
     s->d.n_lights = desc->n_lights;
     s->d.cam = desc->camera;
     for (int c = 0; c < 3; ++c) s->d.background[c] = desc->background[c];
+    if (const char *e = getenv("RTGPU_L1_CARVEOUT")) { /* A/B: shared-memory carveout of the traversal kernels, percent */
+        int pct = atoi(e);
+        cudaFuncSetAttribute(k_extend, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_trace_extend, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaGetLastError();
+    }
     *out = s;
     return RTGPU_OK;
 }
