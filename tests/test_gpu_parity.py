@@ -382,3 +382,20 @@ def test_fuzz_random_graphs(seed):
     g2, _ = rt.GpuScene(s.lower(elide_singletons=False), device=0).trace_batch(rays, keys)
     for f in ("hit", "gid", "face", "inst", "rng_pos"):
         assert np.array_equal(g[f], g2[f])
+
+
+@pytest.mark.parametrize("name", ["cornell_box", "random_scene", "obj_cornell", "cornell_book3"])
+def test_t_and_p_are_bit_identical_without_media(name):
+    """+, -, *, /, sqrt are IEEE-exact on both sides and the operation order is the reference's, so for scenes
+    without a ConstantMedium (whose log() differs by <= 1 ulp between CUDA and glibc) t, p and the normal are
+    not merely within 1e-5: they are the same doubles.  u, v go through acos/atan2 and are compared to 1e-9."""
+    s, orc, gpu = get(name)
+    w = h = 64
+    cam, _ = gpu.camera_rays(w, h, 0, w * h, 2)
+    rays = np.concatenate([cam, orc.dump_rays(w, h, 2, 1, 1 << 13), orc.dump_rays(w, h, 2, 4, 1 << 12)])
+    g, _ = gpu.trace_batch(rays)
+    o = orc.trace_batch(rays)
+    compare_hits(g, o)
+    m = o["hit"] == 1
+    for f in ("t", "p", "n"):
+        assert np.array_equal(g[f][m], o[f][m]), f
