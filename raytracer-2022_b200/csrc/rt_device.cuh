@@ -432,6 +432,9 @@ __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_
 #ifndef RT_MEDIUM_QUORUM
 #define RT_MEDIUM_QUORUM 8 /* lanes that must stand on a ConstantMedium before it runs (1 = no hold) */
 #endif
+#ifndef RT_PREFETCH_AHEAD
+#define RT_PREFETCH_AHEAD 16384 /* rays ahead of the fetch counter pulled into L2 at every refill (0 = off; +1 %) */
+#endif
 #ifndef RT_NODE_UNROLL
 #define RT_NODE_UNROLL 2 /* boxes a lane may test under one vote (A/B on the B200: 2 is +2..7 %) */
 #endif
@@ -449,7 +452,9 @@ __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_
  * results are identical to the sequential walk.
  * IO: load(idx, o, d, tm, tmin, tmax), draw() -> next uniform of the current ray, store(idx, Closest). */
 #ifdef RT_DEBUG_COUNTERS
-__device__ unsigned long long g_dbg[16]; /* [k] rounds that picked phase k, [8+k] lanes that ran in them */
+/* [0] NODE rounds, [8] lanes that ran in them, [1..4] leaf ops by phase;  warp clocks: [16] refill/start, [17] NODE rounds,
+ * [18] leaf section;  [20+ph] clocks the lanes of leaf phase ph spent in their case, [25+ph] how often that case ran */
+__device__ unsigned long long g_dbg[32];
 #endif
 template <typename IO>
 __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_ops, uint32_t n, uint32_t *fetch, IO &io) {
@@ -458,7 +463,14 @@ __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_
     SavedRays stk;
     bool active = false, exhausted = false;
     uint32_t idx = 0;
+#ifdef RT_DEBUG_COUNTERS
+    unsigned long long dbg_acc[32]; /* per lane, flushed once at the end: atomics inside the loop would distort the clocks */
+    for (int k = 0; k < 32; ++k) dbg_acc[k] = 0;
+#endif
     for (;;) {
+#ifdef RT_DEBUG_COUNTERS
+        long long c0 = clock64();
+#endif
         uint32_t idle = __ballot_sync(0xffffffffu, !active);
         if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= RT_EXTEND_REFILL)) {
             int leader = __ffs(idle) - 1;
@@ -468,6 +480,9 @@ __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_
             exhausted = base + (uint32_t)__popc(idle) >= n;
             if (!active) {
                 idx = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+#if RT_PREFETCH_AHEAD > 0
+                if (idx + RT_PREFETCH_AHEAD < n) io.prefetch(idx + RT_PREFETCH_AHEAD);
+#endif
                 if (idx < n) {
                     V3 o, d;
                     double tm, tmin, tmax;
@@ -486,14 +501,18 @@ __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_
         const uint32_t n_active = 32u - (uint32_t)__popc(idle);
         const uint32_t node_quorum = max(1u, (n_active * RT_NODE_QUORUM_PCT) / 100u);
         bool node_ran = false;
+#ifdef RT_DEBUG_COUNTERS
+        long long c1 = clock64();
+        if (lane == 0) dbg_acc[16] += (unsigned long long)(c1 - c0);
+#endif
 #pragma unroll 1
         for (;;) {
             bool in_node = active && tr.phase() == PH_NODE;
             uint32_t m = __ballot_sync(0xffffffffu, in_node);
 #ifdef RT_DEBUG_COUNTERS
             if (lane == 0 && (uint32_t)__popc(m) >= node_quorum) {
-                atomicAdd(&g_dbg[0], 1ull);
-                atomicAdd(&g_dbg[8], (unsigned long long)__popc(m));
+                dbg_acc[0] += 1ull;
+                dbg_acc[8] += (unsigned long long)__popc(m);
             }
 #endif
             if ((uint32_t)__popc(m) < node_quorum) break;
@@ -516,6 +535,10 @@ __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_
          * instructions (two boundary hits, Philox, log) and every ray of a foggy scene meets it, so the
          * lanes standing on one pile up quickly; they run together instead of 5 at a time. */
         bool hold = false;
+#ifdef RT_DEBUG_COUNTERS
+        long long c2 = clock64();
+        if (lane == 0) dbg_acc[17] += (unsigned long long)(c2 - c1);
+#endif
 #if RT_MEDIUM_QUORUM > 1
         {
             bool at_medium = active && (tr.h.x & 0xffu) == RTGPU_OP_MEDIUM;
@@ -530,21 +553,47 @@ __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_
 #endif
         if (active && !hold) {
 #ifdef RT_DEBUG_COUNTERS
-            atomicAdd(&g_dbg[tr.phase()], 1ull);
+            dbg_acc[tr.phase()] += 1ull;
+#endif
+#ifdef RT_DEBUG_COUNTERS
+#define RT_TIMED(PH, CALL)                                                                             \
+    {                                                                                                  \
+        long long a_ = clock64();                                                                      \
+        CALL;                                                                                          \
+        long long b_ = clock64();                                                                      \
+        if ((int)lane == __ffs(__activemask()) - 1) { /* the lanes of this case have not reconverged yet */ \
+            dbg_acc[20 + PH] += (unsigned long long)(b_ - a_);                                         \
+            dbg_acc[25 + PH] += 1ull;                                                                  \
+        }                                                                                              \
+    }
+#else
+#define RT_TIMED(PH, CALL) CALL
 #endif
             switch (tr.phase()) {
             case PH_NODE: break; /* below the quorum: waits for the next NODE rounds */
-            case PH_SPHERE: tr.exec_sphere(ts); break;
-            case PH_BOX: tr.exec_box(ts); break;
-            case PH_TRI: tr.exec_tri(ts); break;
-            default: tr.exec_misc<true>(ts, stk, [&]() { return io.draw(); }); break;
+            case PH_SPHERE: RT_TIMED(PH_SPHERE, tr.exec_sphere(ts)); break;
+            case PH_BOX: RT_TIMED(PH_BOX, tr.exec_box(ts)); break;
+            case PH_TRI: RT_TIMED(PH_TRI, tr.exec_tri(ts)); break;
+            default: RT_TIMED(PH_MISC, tr.exec_misc<true>(ts, stk, [&]() { return io.draw(); })); break;
             }
+#undef RT_TIMED
             if (tr.done()) {
                 io.store(idx, tr.best);
                 active = false;
             }
         }
+#ifdef RT_DEBUG_COUNTERS
+        {
+            __syncwarp();
+            long long c3 = clock64();
+            if (lane == 0) dbg_acc[18] += (unsigned long long)(c3 - c2);
+        }
+#endif
     }
+#ifdef RT_DEBUG_COUNTERS
+    for (int k = 0; k < 32; ++k)
+        if (dbg_acc[k]) atomicAdd(&g_dbg[k], dbg_acc[k]);
+#endif
 }
 
 /* ---- HitRecord of the winner (hittable/mod.rs:18-57), rebuilt once per ray ------------------- */

@@ -74,6 +74,28 @@ struct PathQueue {
     RayRec *ray;
     StateRec *st;
 };
+#ifndef RT_STREAM_HINTS
+#define RT_STREAM_HINTS 1 /* queue entries are read once and written once by k_extend: keep them out of L1, which holds the program (+2 %) */
+#endif
+__device__ __forceinline__ double2 ld_stream(const double2 *p) {
+#if RT_STREAM_HINTS
+    double2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
+/* k_extend's read of a queue entry (the shade kernels gather theirs through the class lists and use plain loads) */
+__device__ __forceinline__ RayRec ld_ray_stream(const RayRec *p) {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    double2 a = ld_stream(q), b = ld_stream(q + 1), c = ld_stream(q + 2), d = ld_stream(q + 3);
+    RayRec r;
+    r.ox = a.x; r.oy = a.y; r.oz = b.x; r.dx = b.y; r.dy = c.x; r.dz = c.y; r.tm = d.x;
+    r.pid = (uint32_t)__double2loint(d.y);
+    r.rng = (uint32_t)__double2hiint(d.y);
+    return r;
+}
 __device__ __forceinline__ RayRec ld_ray(const RayRec *p) {
     const double2 *q = reinterpret_cast<const double2 *>(p);
     double2 a = q[0], b = q[1], c = q[2], d = q[3];
@@ -158,7 +180,7 @@ struct QueueIO {
     WaveParams wp;
     uint32_t pid, pos, cur;
     __device__ __forceinline__ void load(uint32_t idx, V3 &o, V3 &d, double &tm, double &tmin, double &tmax) {
-        RayRec rr = ld_ray(q.ray + idx);
+        RayRec rr = ld_ray_stream(q.ray + idx);
         o = v3(rr.ox, rr.oy, rr.oz);
         d = v3(rr.dx, rr.dy, rr.dz);
         tm = rr.tm;
@@ -168,6 +190,8 @@ struct QueueIO {
         pos = rr.rng;
         cur = idx;
     }
+    /* pulls a queue entry that some warp will ask for a few microseconds from now into L2 */
+    __device__ __forceinline__ void prefetch(uint32_t idx) { asm volatile("prefetch.global.L2 [%0];" ::"l"(q.ray + idx)); }
     __device__ __forceinline__ double draw() { /* the path's stream resumes at slot `pos` */
         rt_rng rng;
         path_rng(rng, wp, pid, pos);
@@ -176,9 +200,15 @@ struct QueueIO {
         return u;
     }
     __device__ __forceinline__ void store(uint32_t idx, const Closest &c) {
+#if RT_STREAM_HINTS
+        __stcs(hb.t + idx, c.t);
+        __stcs(hb.op + idx, c.op == RT_NO_HIT ? RT_NO_HIT : (c.op | (c.face << 29)));
+        __stcs(&q.ray[idx].rng, pos);
+#else
         hb.t[idx] = c.t;
         hb.op[idx] = c.op == RT_NO_HIT ? RT_NO_HIT : (c.op | (c.face << 29));
         q.ray[idx].rng = pos;
+#endif
     }
 };
 __global__ void __launch_bounds__(kThreads, RT_EXTEND_MIN_BLOCKS) k_extend(DScene sc, PathQueue q, HitBuf hb, const uint32_t *count,
@@ -489,6 +519,7 @@ struct BatchIO {
         tmax = q.t_max;
         rng.init(keys ? keys[idx] : (uint64_t)idx, 0, 0, RT_DOMAIN_BATCH, 0);
     }
+    __device__ __forceinline__ void prefetch(uint32_t idx) { asm volatile("prefetch.global.L2 [%0];" ::"l"(rays + idx)); }
     __device__ __forceinline__ double draw() { return rng.gen(); }
     __device__ __forceinline__ void store(uint32_t idx, const Closest &c) {
         t[idx] = c.t;
@@ -884,7 +915,15 @@ rtgpu_status run_wave(rtgpu_scene *s, const WaveParams &wp, int max_depth, cudaS
             float ms = 0;
             CK(cudaEventElapsedTime(&ms, s->events[0], s->events[1]));
             wt->ms_other += ms;
+            const bool trace = getenv("RTGPU_TRACE_BOUNCES") != nullptr; /* per-bounce table on stderr (tuning aid) */
             for (int b = 0; b < bounces_run; ++b) {
+                if (trace) {
+                    float me = 0, ms2 = 0;
+                    cudaEventElapsedTime(&me, s->events[2 + 3 * b], s->events[3 + 3 * b]);
+                    cudaEventElapsedTime(&ms2, s->events[3 + 3 * b], s->events[4 + 3 * b]);
+                    fprintf(stderr, "bounce %2d rays %9u extend %8.3f ms (%7.1f Mrays/s) shade %8.3f ms\n", b, s->counts_host[b], me,
+                            s->counts_host[b] / (me * 1e3 + 1e-9), ms2);
+                }
                 if (b > 0) { /* sort between the previous shade and this extend */
                     CK(cudaEventElapsedTime(&ms, s->events[1 + 3 * b], s->events[2 + 3 * b]));
                     wt->ms_other += ms;
@@ -904,10 +943,10 @@ rtgpu_status run_wave(rtgpu_scene *s, const WaveParams &wp, int max_depth, cudaS
 extern "C" {
 
 #ifdef RT_DEBUG_COUNTERS
-int rtgpu_debug_counters(unsigned long long out[16], int reset) {
-    cudaMemcpyFromSymbol(out, g_dbg, sizeof(unsigned long long) * 16);
+int rtgpu_debug_counters(unsigned long long out[32], int reset) {
+    cudaMemcpyFromSymbol(out, g_dbg, sizeof(unsigned long long) * 32);
     if (reset) {
-        unsigned long long z[16] = {0};
+        unsigned long long z[32] = {0};
         cudaMemcpyToSymbol(g_dbg, z, sizeof z);
     }
     return 0;

@@ -1,5 +1,5 @@
 """Per-kernel device times of one render (CUDA events inside rtgpu_render) for quick A/B runs on the GPU box."""
-import sys
+import os, sys
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import rtb200 as rt
 
@@ -8,6 +8,7 @@ cfgs = {"final_scene": (800, 800, 8), "random_scene": (400, 225, 64), "cornell_b
 names = sys.argv[1:] or ["final_scene"]
 for name in names:
     w, h, spp = cfgs[name]
+    spp = int(os.environ.get("KT_SPP", spp))  # KT_SPP=24: the wave size bench.py uses
     s = rt.Scene(seed=2022).build_config(name, w / h)
     gpu = rt.GpuScene(s.lower(), 0)
     gpu.render(w, h, 0, spp)  # also sizes the wave buffers

@@ -1,0 +1,56 @@
+// Bit-exactness of div_by() (rt_device.cuh: quotient through the ray's correctly rounded reciprocal) against the
+// IEEE division, over 2^32 pseudo-random operand pairs: uniform mantissas; exponents spread over +-40 around 1,
+// over the whole double range, and the hard cases (numerator an exact multiple of the divisor +- 1 ulp).
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -o div_by_test div_by_test.cu
+#include <cstdio>
+#include "../../raytracer-2022_b200/csrc/rt_device.cuh"
+__device__ __forceinline__ uint64_t mix(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+__device__ __forceinline__ double mk(uint64_t bits, int mode) {
+    uint64_t mant = bits & 0xfffffffffffffull, sign = bits >> 63;
+    int e;
+    if (mode == 0) e = 1023 + (int)((bits >> 52) % 81) - 40;
+    else if (mode == 1) e = (int)((bits >> 52) & 0x7ff);           /* anything, incl. 0 / inf / NaN / subnormal */
+    else e = 1023 + (int)((bits >> 52) % 1201) - 600;               /* around the 2^+-500 guard */
+    return __longlong_as_double((long long)((sign << 63) | ((uint64_t)e << 52) | mant));
+}
+__global__ void test(unsigned long long *bad, unsigned long long *fast, unsigned long long per_thread) {
+    uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long nb = 0, nf = 0;
+    for (unsigned long long k = 0; k < per_thread; ++k) {
+        uint64_t h = mix(id * per_thread + k + 0x9e3779b97f4a7c15ull);
+        int mode = (int)(h % 4);
+        double d = mk(mix(h + 1), mode == 3 ? 0 : mode);
+        double n = mk(mix(h + 2), mode == 3 ? 0 : mode);
+        if (mode == 3) { /* n = RN(m * d) +- {0,1,2} ulp: quotients next to representable numbers and midpoints */
+            double m = mk(mix(h + 3), 0);
+            n = m * d;
+            long long nbits = __double_as_longlong(n) + (long long)(mix(h + 4) % 5) - 2;
+            n = __longlong_as_double(nbits);
+        }
+        double r = 1. / d;
+        uint32_t e = ((uint32_t)__double2hiint(d) >> 20) & 0x7ffu;
+        bool ok = e - 523u <= 1000u;
+        double q = div_by(n, d, r, ok), ref = n / d;
+        bool same = __double_as_longlong(q) == __double_as_longlong(ref) || (q != q && ref != ref);
+        if (!same) ++nb;
+        /* how often the short path is taken */
+        uint32_t eq = ((uint32_t)__double2hiint(ref) >> 20) & 0x7ffu;
+        if (ok && eq - 623u <= 800u) ++nf;
+    }
+    if (nb) atomicAdd(bad, nb);
+    atomicAdd(fast, nf);
+}
+int main() {
+    unsigned long long *d, h[2] = {0, 0};
+    cudaMalloc(&d, 16);
+    cudaMemset(d, 0, 16);
+    const unsigned long long per_thread = 1ull << 12;
+    test<<<1 << 12, 256>>>(d, d + 1, per_thread); /* 2^32 pairs */
+    cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    printf("div_by: %llu mismatches in %llu pairs (%llu through the 3-instruction path)  %s\n", h[0], (1ull << 20) * per_thread, h[1],
+           cudaGetErrorString(cudaGetLastError()));
+    return h[0] != 0;
+}
