@@ -35,7 +35,7 @@ for i in ids[half:]:
 tot = sum(a[1] for a in agg.values())
 with open(f"{out_dir}/{tag}_launches.txt", "w") as f:
     f.write("# ncu --metrics gpu__time_duration.sum,smsp__thread_inst_executed_per_inst_executed.ratio,smsp__inst_executed.sum --clock-control none\n")
-    f.write("# command: python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --spp 24   (C3 final_scene 800x800, 24 spp = one wave)\n")
+    f.write("# command: python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e   (C3 final_scene 800x800, one 96-spp wave per step)\n")
     f.write("# per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.  Timed step only.\n")
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"{k:44s} launches {a[0]:4d}  time {a[1] / 1e6:8.2f} ms  share {a[1] / tot:.3f}  warp-instr {a[2] / 1e6:9.1f} M  "
@@ -47,14 +47,26 @@ print(open(f"{out_dir}/{tag}_launches.txt").read())
 ext_share = agg["k_extend"][1] / tot
 
 # 2. full-set metrics of k_extend
-raw = subprocess.run(["ncu", "-i", f"{G}/prof_extend.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(raw.splitlines()))
-hdr, units = rows[0], rows[1]
+def bench_line(path):
+    for ln in open(path):
+        if ln.startswith("{"):
+            return json.loads(ln)
+    return {}
+
+plain = bench_line(f"{G}/plain2.log")  # the same command without ncu, run just before the capture
+rpb = plain.get("rays_per_bounce", [])
+
+def raw_rows(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    return rows[0], rows[1], rows[2:]
+
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
         "launch__grid_size", "launch__block_size", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__inst_executed.sum", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
@@ -62,18 +74,34 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "smsp__warps_eligible.avg.per_cycle_active",
-        "sass__inst_executed_local_loads", "sass__inst_executed_local_stores"]
+        "sm__icc_request_hit_rate.pct", "sass__inst_executed_local_loads", "sass__inst_executed_local_stores"]
+hdr, units, body = raw_rows(f"{G}/prof_extend.ncu-rep")
+cols = [(f"bounce {b}", r, rpb[b] if b < len(rpb) else None) for b, r in zip((1, 2), body)]
+if os.path.exists(f"{G}/prof_extend_deep.ncu-rep"):
+    h2, u2, b2 = raw_rows(f"{G}/prof_extend_deep.ncu-rep")
+    if b2 and h2 == hdr:
+        row = list(b2[0])
+        sc = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
+        for i, (ua, ub) in enumerate(zip(units, u2)):  # ncu picks the unit per report: bring this one to the first report's units
+            if ua != ub and ua in sc and ub in sc:
+                try:
+                    row[i] = f"{float(row[i]) * sc[ub] / sc[ua]:.6f}"
+                except ValueError:
+                    pass
+        cols.append(("bounce 20", row, None))
 with open(f"{out_dir}/{tag}_k_extend_ncu.txt", "w") as f:
-    f.write("# ncu --set full --clock-control none --import-source on -k regex:k_extend -s 51 -c 2\n")
-    f.write("# = bounces 1 and 2 of the timed step (54 M and 34 M incoherent rays), same bench command as the launch list\n")
+    f.write("# ncu --set full --clock-control none --import-source on -k regex:k_extend -s 51 -c 2   (and -s 70 -c 1 for the deep bounce)\n")
+    f.write("# launches of the timed step of: python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e  (one 96-spp wave)\n")
+    f.write("# columns: " + " | ".join(f"{n}" + (f" ({r / 1e6:.1f} M rays)" if r else "") for n, _, r in cols) + "\n")
     for w in want:
         if w in hdr:
             i = hdr.index(w)
-            f.write(f"{w:85s} {units[i]:16s} {[r[i] for r in rows[2:]]}\n")
+            f.write(f"{w:85s} {units[i]:16s} {[c[1][i] for c in cols]}\n")
 print(open(f"{out_dir}/{tag}_k_extend_ncu.txt").read())
 i_r, i_w = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
 scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-tr = [float(r[i_r]) * scale[units[i_r]] + float(r[i_w]) * scale[units[i_w]] for r in rows[2:]]
-json.dump({"k_extend_dram_bytes_per_launch": tr[0], "captured_launch": "bounce 1 of a 24-spp wave (54.1 M rays)",
+tr = [float(r[i_r]) * scale[units[i_r]] + float(r[i_w]) * scale[units[i_w]] for r in body]
+json.dump({"k_extend_dram_bytes_per_launch": tr[0], "captured_launch": "bounce 1 of the timed step (one 96-spp wave)",
+           "captured_launch_rays": rpb[1] if len(rpb) > 1 else None,
            "all_captured_launches": tr, "k_extend_share_of_step_under_ncu": ext_share,
            "source": f"profiles/{tag}_k_extend_ncu.txt, profiles/{tag}_launches.txt"}, open(f"{out_dir}/roofline_ncu.json", "w"), indent=1)
