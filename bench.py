@@ -321,8 +321,8 @@ def main():
             "config": {"workload": args.workload, "scene": scene_name, "width": w, "height": h, "spp_per_step_per_gpu": spp,
                        "max_depth": args.depth, "seed": args.seed, "parallelism": f"spp-sharded x{world}, 1 NCCL reduce/step",
                        "paths_in_flight_per_gpu": w * h * spp,
-                       "wave_state_bytes_per_gpu": w * h * spp * 272,
-                       "l2": "wave state (272 B x paths = GBs per step) exceeds the 126 MB L2; scene arrays are L2-resident by design"},
+                       "wave_state_bytes_per_gpu": w * h * spp * 276,
+                       "l2": "wave state (276 B x paths = GBs per step) exceeds the 126 MB L2; scene arrays are L2-resident by design"},
             "samples_per_s": samples_all / (ms * 1e-3),
             "rays_per_sample": rays_all / max(samples_all, 1),
             "clocks": clocks,

@@ -124,7 +124,9 @@ __device__ __forceinline__ void st_beta(StateRec *p, V3 b) {
 }
 struct HitBuf {
     double *t;
-    uint32_t *op; /* op index | box face << 29; RT_NO_HIT = miss */
+    uint32_t *op;  /* op index | box face << 29; RT_NO_HIT = miss */
+    uint32_t *rng; /* the path's Philox slot after the walk (media draw): a 4-byte array of its own -- written back into the
+                      64-byte ray record it dirtied one 32-byte sector per ray, 28 B/ray of DRAM writes for nothing */
 };
 struct WaveParams {
     uint64_t seed;
@@ -203,11 +205,11 @@ struct QueueIO {
 #if RT_STREAM_HINTS
         __stcs(hb.t + idx, c.t);
         __stcs(hb.op + idx, c.op == RT_NO_HIT ? RT_NO_HIT : (c.op | (c.face << 29)));
-        __stcs(&q.ray[idx].rng, pos);
+        __stcs(hb.rng + idx, pos);
 #else
         hb.t[idx] = c.t;
         hb.op[idx] = c.op == RT_NO_HIT ? RT_NO_HIT : (c.op | (c.face << 29));
-        q.ray[idx].rng = pos;
+        hb.rng[idx] = pos;
 #endif
     }
 };
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(DScene sc, PathQueue qi
             beta = ld_beta(qin.st + i);
             pid = rr.pid;
             rt_rng rng;
-            path_rng(rng, wp, pid, rr.rng);
+            path_rng(rng, wp, pid, hb.rng[i]);
             V3 contrib;
             alive = shade_segment<CLS>(sc, r, hb.t[i], hb.op[i], rng, beta, next, contrib);
             pos = rng.pos;
@@ -783,8 +785,8 @@ rtgpu_status ensure_wave(rtgpu_scene *s, size_t n_paths, int max_depth) {
     s->wave_mem = nullptr;
     s->cap = 0;
     size_t n = (n_paths + 255) & ~(size_t)255;
-    /* per path: 2 queues x (64 B ray + 32 B state) + hit (double + u32) + contrib (3 doubles) + path_len + sort/class lists */
-    size_t bytes = n * (2 * (sizeof(RayRec) + sizeof(StateRec)) + 8 + 4 + 3 * 8 + 4 + 4 * 4 + kClasses * 4) + 256;
+    /* per path: 2 queues x (64 B ray + 32 B state) + hit (double + u32 + u32 rng slot) + contrib (3 doubles) + path_len + sort/class lists */
+    size_t bytes = n * (2 * (sizeof(RayRec) + sizeof(StateRec)) + 8 + 4 + 4 + 3 * 8 + 4 + 4 * 4 + kClasses * 4) + 256;
     CK(cudaMalloc(&s->wave_mem, bytes));
     char *p = static_cast<char *>(s->wave_mem);
     auto take_d = [&](double *&dst) { dst = reinterpret_cast<double *>(p); p += n * 8; };
@@ -799,6 +801,7 @@ rtgpu_status ensure_wave(rtgpu_scene *s, size_t n_paths, int max_depth) {
     take_d(s->hb.t);
     take_d(s->cx); take_d(s->cy); take_d(s->cz);
     take_u(s->hb.op);
+    take_u(s->hb.rng);
     take_u(s->path_len);
     s->class_idx = reinterpret_cast<uint32_t *>(p);
     p += n * 4 * kClasses;
