@@ -214,6 +214,7 @@ def main():
     accum = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
     spp = args.spp
     step_no = [0]
+    wave_paths = [w * h * spp]  # one wave per step; halved if the device cannot hold its 276 B per path
 
     def step(g=gpu):
         """one pass of the hot path: this rank's spp shard of the frame, then the reduce"""
@@ -221,7 +222,7 @@ def main():
         step_no[0] += 1
         b, e = mg.step_sample_range(i, rank, world, spp)
         _, st = g.render(w, h, b, e, max_depth=args.depth, seed=args.seed, accum_ptr=accum.data_ptr(), stream=stream,
-                         max_paths_in_flight=w * h * spp)
+                         max_paths_in_flight=wave_paths[0])
         mg.reduce_to_root(accum, world)
         return st
 
@@ -230,6 +231,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    while True:  # size the wave to the device once, before anything is timed
+        try:
+            step()
+            break
+        except rt.RtError as e:
+            if "memory" not in str(e).lower() or wave_paths[0] <= w * h:
+                raise
+            wave_paths[0] = max(w * h, wave_paths[0] // 2)
+            print(f"bench: wave does not fit this device, retrying with {wave_paths[0]} paths in flight", file=sys.stderr)
     for _ in range(args.warmup):
         step()
     # ---- timed region: K steps, scene resident in HBM ----
@@ -320,8 +330,8 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "scene": scene_name, "width": w, "height": h, "spp_per_step_per_gpu": spp,
                        "max_depth": args.depth, "seed": args.seed, "parallelism": f"spp-sharded x{world}, 1 NCCL reduce/step",
-                       "paths_in_flight_per_gpu": w * h * spp,
-                       "wave_state_bytes_per_gpu": w * h * spp * 276,
+                       "paths_in_flight_per_gpu": wave_paths[0],
+                       "wave_state_bytes_per_gpu": wave_paths[0] * 276,
                        "l2": "wave state (276 B x paths = GBs per step) exceeds the 126 MB L2; scene arrays are L2-resident by design"},
             "samples_per_s": samples_all / (ms * 1e-3),
             "rays_per_sample": rays_all / max(samples_all, 1),
