@@ -231,7 +231,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    while True:  # size the wave to the device once, before anything is timed
+    while True:  # the first warm-up step also sizes the wave to the device, before anything is timed
         try:
             step()
             break
@@ -240,7 +240,7 @@ def main():
                 raise
             wave_paths[0] = max(w * h, wave_paths[0] // 2)
             print(f"bench: wave does not fit this device, retrying with {wave_paths[0]} paths in flight", file=sys.stderr)
-    for _ in range(args.warmup):
+    for _ in range(args.warmup - 1):
         step()
     # ---- timed region: K steps, scene resident in HBM ----
     sampler = ClockSampler(local)
