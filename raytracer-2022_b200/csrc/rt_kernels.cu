@@ -180,8 +180,10 @@ struct QueueIO {
     PathQueue q;
     HitBuf hb;
     WaveParams wp;
+    const uint32_t *perm; /* sorted order -> queue entry (ray reordering without moving the records), or nullptr */
     uint32_t pid, pos, cur;
     __device__ __forceinline__ void load(uint32_t idx, V3 &o, V3 &d, double &tm, double &tmin, double &tmax) {
+        if (perm) idx = __ldg(perm + idx);
         RayRec rr = ld_ray_stream(q.ray + idx);
         o = v3(rr.ox, rr.oy, rr.oz);
         d = v3(rr.dx, rr.dy, rr.dz);
@@ -193,7 +195,9 @@ struct QueueIO {
         cur = idx;
     }
     /* pulls a queue entry that some warp will ask for a few microseconds from now into L2 */
-    __device__ __forceinline__ void prefetch(uint32_t idx) { asm volatile("prefetch.global.L2 [%0];" ::"l"(q.ray + idx)); }
+    __device__ __forceinline__ void prefetch(uint32_t idx) {
+        if (!perm) asm volatile("prefetch.global.L2 [%0];" ::"l"(q.ray + idx));
+    }
     __device__ __forceinline__ double draw() { /* the path's stream resumes at slot `pos` */
         rt_rng rng;
         path_rng(rng, wp, pid, pos);
@@ -201,7 +205,8 @@ struct QueueIO {
         pos = rng.pos;
         return u;
     }
-    __device__ __forceinline__ void store(uint32_t idx, const Closest &c) {
+    __device__ __forceinline__ void store(uint32_t, const Closest &c) {
+        const uint32_t idx = cur;
 #if RT_STREAM_HINTS
         __stcs(hb.t + idx, c.t);
         __stcs(hb.op + idx, c.op == RT_NO_HIT ? RT_NO_HIT : (c.op | (c.face << 29)));
@@ -214,12 +219,99 @@ struct QueueIO {
     }
 };
 __global__ void __launch_bounds__(kThreads, RT_EXTEND_MIN_BLOCKS) k_extend(DScene sc, PathQueue q, HitBuf hb, const uint32_t *count,
-                                                                           uint32_t *fetch, WaveParams wp) {
+                                                                           uint32_t *fetch, WaveParams wp, const uint32_t *perm) {
     QueueIO io;
     io.q = q;
     io.hb = hb;
     io.wp = wp;
+    io.perm = perm;
     extend_warp_loop(trav_of(sc), sc.n_ops, *count, fetch, io);
+}
+
+/* ---- ray reordering between bounces ---------------------------------------------------------------
+ * Rays that start close together and point the same way walk nearly the same ops in the same order (the traversal
+ * order is ray-independent), so a warp of neighbours in a sorted order diverges far less: the box rounds of k_extend
+ * run with 5-6 of 32 lanes on bounce rays in arrival order and ~16 on camera rays.  The records do not move:
+ *   - the shade kernels write a 32-bit key next to every ray they enqueue (ray_sort_key: origin cell, Morton order,
+ *     then direction octant and a 2 x 3-bit direction) -- no extra pass over the queue;
+ *   - cub::DeviceRadixSort sorts (key, entry index) pairs;
+ *   - k_extend takes its rays through the sorted index (QueueIO::perm) and writes its results to the entry's own
+ *     slot, so classify / shade are unaffected and the image does not depend on the order at all.
+ * The grid of origin cells is fixed per wave from the first hit points (mean +- 2.5 sigma per axis: the global fog
+ * scatters a few rays very far away; min/max bounds would waste the key bits on empty space). */
+struct SortGrid {
+    float lo[3], inv[3];
+};
+#ifndef RT_SORT_CELL_BITS
+#define RT_SORT_CELL_BITS 7
+#endif
+constexpr int kSortKeyBits = 3 * RT_SORT_CELL_BITS + 3 + 8;
+__device__ __forceinline__ uint32_t spread_bits(uint32_t v) { /* RT_SORT_CELL_BITS bits -> every third bit */
+    uint32_t r = 0;
+#pragma unroll
+    for (int b = 0; b < RT_SORT_CELL_BITS; ++b) r |= ((v >> b) & 1u) << (3 * b);
+    return r;
+}
+__device__ __forceinline__ uint32_t ray_sort_key(const SortGrid &g, V3 ro, V3 rd) {
+    float o[3] = {(float)ro.x, (float)ro.y, (float)ro.z};
+    float d[3] = {(float)rd.x, (float)rd.y, (float)rd.z};
+    uint32_t cell[3];
+    const float top = (float)((1 << RT_SORT_CELL_BITS) - 1);
+    for (int c = 0; c < 3; ++c) cell[c] = (uint32_t)fminf(fmaxf((o[c] - g.lo[c]) * g.inv[c], 0.f), top); /* NaN -> 0 */
+    uint32_t morton = spread_bits(cell[0]) | (spread_bits(cell[1]) << 1) | (spread_bits(cell[2]) << 2);
+    uint32_t oct = (d[0] < 0.f ? 1u : 0u) | (d[1] < 0.f ? 2u : 0u) | (d[2] < 0.f ? 4u : 0u);
+    float ax = fabsf(d[0]), ay = fabsf(d[1]), az = fabsf(d[2]);
+    float m = fmaxf(ax, fmaxf(ay, az));
+    float sc = m > 0.f ? 7.999f / m : 0.f;
+    uint32_t major = (ax >= ay && ax >= az) ? 0u : (ay >= az ? 1u : 2u);
+    float u = major == 0 ? ay : ax, v = major == 2 ? ay : az;
+    uint32_t dq = (major << 6) | ((uint32_t)fminf(u * sc, 7.f) << 3) | (uint32_t)fminf(v * sc, 7.f); /* 2 + 3 + 3 bits */
+    return (morton << 11) | (oct << 8) | dq;
+}
+/* moments of the first hit points of a wave (every 8th camera ray) */
+__global__ void k_sort_moments(PathQueue q, HitBuf hb, const uint32_t *count, double *moments /* sum xyz, sum xyz^2, n */) {
+    uint32_t n = *count;
+    double s1[3] = {0., 0., 0.}, s2[3] = {0., 0., 0.}, cnt = 0.;
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * 8u; i < n; i += stride * 8u) {
+        if (hb.op[i] == RT_NO_HIT) continue;
+        RayRec rr = ld_ray(q.ray + i);
+        double t = hb.t[i];
+        double x = rr.ox + t * rr.dx, y = rr.oy + t * rr.dy, z = rr.oz + t * rr.dz;
+        if (fabs(x) < 1e30 && fabs(y) < 1e30 && fabs(z) < 1e30) {
+            s1[0] += x; s1[1] += y; s1[2] += z;
+            s2[0] += x * x; s2[1] += y * y; s2[2] += z * z;
+            cnt += 1.;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        for (int c = 0; c < 3; ++c) {
+            s1[c] += __shfl_xor_sync(0xffffffffu, s1[c], o);
+            s2[c] += __shfl_xor_sync(0xffffffffu, s2[c], o);
+        }
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0 && cnt > 0.) {
+        for (int c = 0; c < 3; ++c) {
+            atomicAdd(moments + c, s1[c]);
+            atomicAdd(moments + 3 + c, s2[c]);
+        }
+        atomicAdd(moments + 6, cnt);
+    }
+}
+__global__ void k_sort_grid(const double *moments, SortGrid *g) {
+    for (int c = 0; c < 3; ++c) {
+        double cnt = fmax(moments[6], 1.);
+        double mean = moments[c] / cnt;
+        double sd = sqrt(fmax(moments[3 + c] / cnt - mean * mean, 0.));
+        g->lo[c] = (float)(mean - 2.5 * sd);
+        float ext = (float)(5.0 * sd);
+        g->inv[c] = ext > 0.f ? ((float)(1 << RT_SORT_CELL_BITS) - 0.001f) / ext : 0.f;
+    }
+}
+__global__ void k_iota(uint32_t *p, uint32_t n) {
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = i;
 }
 
 /* ---- shading, split by material class ------------------------------------------------------------
@@ -338,7 +430,7 @@ __device__ __forceinline__ bool shade_segment(const DScene &sc, const Ray &r, do
 template <int CLS>
 __global__ void __launch_bounds__(kShadeThreads) k_shade(DScene sc, PathQueue qin, HitBuf hb, PathQueue qout, const uint32_t *class_count,
                                                     const uint32_t *class_idx, uint32_t *count_out, double *cx, double *cy, double *cz,
-                                                    uint32_t *path_len, WaveParams wp, uint32_t bounce) {
+                                                    uint32_t *path_len, WaveParams wp, uint32_t bounce, const SortGrid *grid, uint32_t *keys_out) {
     uint32_t n = class_count[CLS];
     uint32_t stride = gridDim.x * blockDim.x;
     uint32_t lane = threadIdx.x & 31u;
@@ -382,106 +474,10 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(DScene sc, PathQueue qi
                     uint32_t k = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
                     st_ray(qout.ray + k, next.o, next.d, next.tm, pid, pos);
                     st_beta(qout.st + k, beta);
+                    if (keys_out) keys_out[k] = ray_sort_key(*grid, next.o, next.d);
                 }
             }
         }
-    }
-}
-
-/* ---- ray reordering between bounces: rays that start close together and point the same way walk
- * nearly the same ops in the same order (the traversal order is ray-independent), so a warp of
- * neighbours in the sorted queue diverges far less.  key = Morton(origin, 7 bits/axis) : direction
- * (octant + 2 x 3 bits). ------------------------------------------------------------------------ */
-__device__ __forceinline__ uint32_t f2ord(float f) { /* order-preserving float -> uint */
-    uint32_t u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float ord2f(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
-/* robust origin bounds: mean +- 2.5 sigma per axis (a ConstantMedium as large as the world scatters a few
- * rays very far away; min/max bounds would waste the key bits on empty space) */
-__global__ void k_sort_bounds(PathQueue q, const uint32_t *count, double *moments /* sum xyz, sum xyz^2, n */) {
-    uint32_t n = *count;
-    double s1[3] = {0., 0., 0.}, s2[3] = {0., 0., 0.}, cnt = 0.;
-    uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride * 4) { /* every 4th stripe: a sample is enough */
-        double x = q.ray[i].ox, y = q.ray[i].oy, z = q.ray[i].oz;
-        if (fabs(x) < 1e30 && fabs(y) < 1e30 && fabs(z) < 1e30) {
-            s1[0] += x; s1[1] += y; s1[2] += z;
-            s2[0] += x * x; s2[1] += y * y; s2[2] += z * z;
-            cnt += 1.;
-        }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        for (int c = 0; c < 3; ++c) {
-            s1[c] += __shfl_xor_sync(0xffffffffu, s1[c], o);
-            s2[c] += __shfl_xor_sync(0xffffffffu, s2[c], o);
-        }
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    }
-    if ((threadIdx.x & 31) == 0 && cnt > 0.) {
-        for (int c = 0; c < 3; ++c) {
-            atomicAdd(moments + c, s1[c]);
-            atomicAdd(moments + 3 + c, s2[c]);
-        }
-        atomicAdd(moments + 6, cnt);
-    }
-}
-__device__ __forceinline__ uint32_t spread7(uint32_t v) { /* 7 bits -> every third bit */
-    uint32_t r = 0;
-#pragma unroll
-    for (int b = 0; b < 7; ++b) r |= ((v >> b) & 1u) << (3 * b);
-    return r;
-}
-__global__ void k_sort_keys(PathQueue q, const uint32_t *count, const double *moments, uint32_t *keys, uint32_t *idx, uint32_t n_pad) {
-    uint32_t n = *count;
-    float lo[3], inv[3];
-    for (int c = 0; c < 3; ++c) {
-        double cnt = fmax(moments[6], 1.);
-        double mean = moments[c] / cnt;
-        double var = fmax(moments[3 + c] / cnt - mean * mean, 0.);
-        double sd = sqrt(var);
-        lo[c] = (float)(mean - 2.5 * sd);
-        float ext = (float)(5.0 * sd);
-        inv[c] = ext > 0.f ? 127.999f / ext : 0.f;
-    }
-    uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
-        uint32_t key = 0xffffffffu;
-        if (i < n) {
-            RayRec rr = ld_ray(q.ray + i);
-            float o[3] = {(float)rr.ox, (float)rr.oy, (float)rr.oz};
-            float d[3] = {(float)rr.dx, (float)rr.dy, (float)rr.dz};
-            uint32_t cell[3];
-            for (int c = 0; c < 3; ++c) {
-                float t = (o[c] - lo[c]) * inv[c];
-                cell[c] = (uint32_t)fminf(fmaxf(t, 0.f), 127.f);
-            }
-            uint32_t morton = spread7(cell[0]) | (spread7(cell[1]) << 1) | (spread7(cell[2]) << 2);
-            uint32_t oct = (d[0] < 0.f ? 1u : 0u) | (d[1] < 0.f ? 2u : 0u) | (d[2] < 0.f ? 4u : 0u);
-            float ax = fabsf(d[0]), ay = fabsf(d[1]), az = fabsf(d[2]);
-            float m = fmaxf(ax, fmaxf(ay, az));
-            float s = m > 0.f ? 7.999f / m : 0.f;
-            uint32_t major = (ax >= ay && ax >= az) ? 0u : (ay >= az ? 1u : 2u);
-            float u = major == 0 ? ay : ax, v = major == 2 ? ay : az;
-            uint32_t dq = (major << 6) | ((uint32_t)(u * s) << 3) | (uint32_t)(v * s); /* 2 + 3 + 3 bits */
-            key = (morton << 11) | (oct << 8) | dq;
-            key &= 0x7fffffffu;
-        }
-        keys[i] = key;
-        idx[i] = i;
-    }
-}
-__global__ void k_sort_gather(PathQueue src, PathQueue dst, const uint32_t *count, const uint32_t *idx) {
-    uint32_t n = *count;
-    uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-        uint32_t i = idx[j];
-        const uint4 *a = reinterpret_cast<const uint4 *>(src.ray + i);
-        uint4 *b = reinterpret_cast<uint4 *>(dst.ray + j);
-        b[0] = a[0]; b[1] = a[1]; b[2] = a[2]; b[3] = a[3];
-        const uint4 *c = reinterpret_cast<const uint4 *>(src.st + i);
-        uint4 *e = reinterpret_cast<uint4 *>(dst.st + j);
-        e[0] = c[0]; e[1] = c[1];
     }
 }
 
@@ -629,9 +625,10 @@ struct WaveRes {
     float *accum_dev = nullptr;
     size_t accum_cap = 0;
     std::vector<cudaEvent_t> events;
-    /* ray reordering */
+    /* ray reordering: keys written by the shade kernels, their sorted copy, iota and the sorted entry indices */
     uint32_t *sort_keys[2] = {nullptr, nullptr}, *sort_idx[2] = {nullptr, nullptr};
-    double *sort_bounds = nullptr;
+    double *sort_bounds = nullptr; /* 7 moments, then the SortGrid */
+    bool iota_ready = false;
     void *sort_temp = nullptr;
     size_t sort_temp_bytes = 0;
     void release() {
@@ -652,8 +649,8 @@ struct rtgpu_scene : WaveRes {
     std::vector<void *> allocs;
     const uint8_t *mat_class = nullptr; /* device: shade class per material */
     bool class_present[8] = {true, false, false, false, false, false, false, false};
-    int sort_mode = 0; /* RTGPU_SORT_RAYS=1: reorder rays between bounces */
-    uint32_t sort_min = 1u << 16;
+    int sort_mode = 1;          /* RTGPU_SORT_RAYS=0: never reorder rays between bounces */
+    uint32_t sort_min = 1u << 18; /* RTGPU_SORT_MIN: smallest bounce worth a sort (A/B on the B200: 100 K .. 2 M within 1 %) */
 };
 
 namespace {
@@ -806,10 +803,11 @@ rtgpu_status ensure_wave(rtgpu_scene *s, size_t n_paths, int max_depth) {
     s->class_idx = reinterpret_cast<uint32_t *>(p);
     p += n * 4 * kClasses;
     take_u(s->sort_keys[0]); take_u(s->sort_keys[1]); take_u(s->sort_idx[0]); take_u(s->sort_idx[1]);
-    s->sort_bounds = reinterpret_cast<double *>(p + ((8 - ((size_t)p & 7)) & 7));
+    s->sort_bounds = reinterpret_cast<double *>(p + ((8 - ((size_t)p & 7)) & 7)); /* 7 doubles + SortGrid: inside the 256 spare bytes */
+    s->iota_ready = false;
     {
         size_t need = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, need, s->sort_keys[0], s->sort_keys[1], s->sort_idx[0], s->sort_idx[1], (int)n, 0, 31);
+        cub::DeviceRadixSort::SortPairs(nullptr, need, s->sort_keys[0], s->sort_keys[1], s->sort_idx[0], s->sort_idx[1], (int)n, 0, kSortKeyBits);
         if (need > s->sort_temp_bytes) {
             if (s->sort_temp) cudaFree(s->sort_temp);
             s->sort_temp = nullptr;
@@ -853,43 +851,53 @@ rtgpu_status run_wave(rtgpu_scene *s, const WaveParams &wp, int max_depth, cudaS
     if (timing) CK(cudaEventRecord(s->events[ev++], stream));
     int cur = 0; /* queue that holds the rays of the current bounce */
     int bounces_run = 0;
+    /* bounce rays are sorted (see "ray reordering") while a bounce carries at least sort_min of them */
+    bool sorting = s->sort_mode != 0 && wp.n_paths >= s->sort_min && max_depth > 1;
+    SortGrid *grid = reinterpret_cast<SortGrid *>(s->sort_bounds + 8);
+    if (sorting && !s->iota_ready) {
+        k_iota<<<blocks, 256, 0, stream>>>(s->sort_idx[0], (uint32_t)s->cap);
+        s->iota_ready = true;
+    }
     for (int b = 0; b < max_depth; ++b) {
-        if (!s->sort_mode && b > 0 && (b % 8) == 0) {
-            /* every 8 bounces: is anything still alive? (one 4-byte readback) */
-            CK(cudaMemcpyAsync(s->counts_host + b, s->counts + b, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-            CK(cudaStreamSynchronize(stream));
-            if (s->counts_host[b] == 0) break;
-        }
-        if (s->sort_mode && b >= 1) {
-            /* the queue length is needed on the host to size the sort (one small readback per bounce) */
+        const uint32_t *perm = nullptr;
+        if (sorting && b >= 1) {
+            /* the queue length is needed on the host to size the sort: one 4-byte readback per sorted bounce */
             CK(cudaMemcpyAsync(s->counts_host + b, s->counts + b, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
             uint32_t nb = s->counts_host[b];
             if (nb == 0) break;
             if (nb >= s->sort_min) {
-                CK(cudaMemsetAsync(s->sort_bounds, 0, 7 * sizeof(double), stream));
-                k_sort_bounds<<<blocks, kThreads, 0, stream>>>(s->q[cur], s->counts + b, s->sort_bounds);
-                k_sort_keys<<<blocks, kThreads, 0, stream>>>(s->q[cur], s->counts + b, s->sort_bounds, s->sort_keys[0], s->sort_idx[0], nb);
                 size_t tb = s->sort_temp_bytes;
                 CK(cub::DeviceRadixSort::SortPairs(s->sort_temp, tb, s->sort_keys[0], s->sort_keys[1], s->sort_idx[0], s->sort_idx[1],
-                                                   (int)nb, 0, 31, stream));
-                k_sort_gather<<<blocks, kThreads, 0, stream>>>(s->q[cur], s->q[cur ^ 1], s->counts + b, s->sort_idx[1]);
-                cur ^= 1;
+                                                   (int)nb, 0, kSortKeyBits, stream));
+                perm = s->sort_idx[1];
                 if (wt) wt->launches += 3;
+            } else {
+                sorting = false; /* queues only shrink: the rest of the wave runs in arrival order */
             }
+        } else if (b > 0 && (b % 8) == 0) {
+            /* every 8 bounces: is anything still alive? (one 4-byte readback) */
+            CK(cudaMemcpyAsync(s->counts_host + b, s->counts + b, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            if (s->counts_host[b] == 0) break;
         }
         PathQueue &qin = s->q[cur], &qout = s->q[cur ^ 1];
         if (timing) CK(cudaEventRecord(s->events[ev++], stream));
-        k_extend<<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->counts + b, s->counts + s->max_counts + b, wp);
+        k_extend<<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->counts + b, s->counts + s->max_counts + b, wp, perm);
         CK(cudaGetLastError()); /* a failed extend launch must not let the shade kernels read stale hits */
         if (timing) CK(cudaEventRecord(s->events[ev++], stream));
+        if (sorting && b == 0) { /* the origin grid of this wave's keys, from the first hit points */
+            CK(cudaMemsetAsync(s->sort_bounds, 0, 7 * sizeof(double), stream));
+            k_sort_moments<<<blocks, kThreads, 0, stream>>>(qin, s->hb, s->counts + b, s->sort_bounds);
+            k_sort_grid<<<1, 1, 0, stream>>>(s->sort_bounds, grid);
+        }
         {
             uint32_t *cc = s->class_count + 8 * b;
             uint32_t *pl = want_len ? s->path_len : nullptr;
             uint32_t cap = (uint32_t)s->cap;
             k_classify<<<blocks, 256, 0, stream>>>(s->d, s->mat_class, s->hb, s->counts + b, cc, s->class_idx, cap);
 #define RT_SHADE(C) k_shade<C><<<kSMs * RT_SHADE_BLOCKS_PER_SM, kShadeThreads, 0, stream>>>(s->d, qin, s->hb, qout, cc, s->class_idx + (size_t)C * cap, s->counts + b + 1, \
-                                                                s->cx, s->cy, s->cz, pl, wp, (uint32_t)b)
+                                                                s->cx, s->cy, s->cz, pl, wp, (uint32_t)b, grid, sorting ? s->sort_keys[0] : nullptr)
             int n_launched = 0;
             RT_SHADE(0);
             if (s->class_present[1]) { RT_SHADE(1); ++n_launched; }

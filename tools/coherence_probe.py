@@ -43,6 +43,22 @@ key = ((cell[:, 0] * 64 + cell[:, 1]) * 64 + cell[:, 2]) * 8 + octant
 run("secondary rays, sorted cell64+octant", sec[np.argsort(key, kind="stable")])
 key2 = octant * (1 << 20) + ((cell[:, 0] * 64 + cell[:, 1]) * 64 + cell[:, 2])
 run("secondary rays, sorted octant+cell64", sec[np.argsort(key2, kind="stable")])
+# more keys: how fine must origin / direction be, and which goes first?
+def cells(bits):
+    return np.clip(((o - lo) / ext * (1 << bits)).astype(np.int64), 0, (1 << bits) - 1)
+def lin(c, bits):
+    return (c[:, 0] << (2 * bits)) | (c[:, 1] << bits) | c[:, 2]
+dn = d / np.linalg.norm(d, axis=1, keepdims=True)
+theta = np.clip(((np.arccos(np.clip(dn[:, 1], -1, 1)) / np.pi) * 16).astype(np.int64), 0, 15)
+phi = np.clip((((np.arctan2(dn[:, 2], dn[:, 0]) + np.pi) / (2 * np.pi)) * 32).astype(np.int64), 0, 31)
+dir9 = theta * 32 + phi
+for label, k in (("cell32, then direction 16x32", lin(cells(5), 5) * 512 + dir9),
+                 ("cell16, then direction 16x32", lin(cells(4), 4) * 512 + dir9),
+                 ("cell8, then direction 16x32", lin(cells(3), 3) * 512 + dir9),
+                 ("direction 16x32, then cell32", dir9 * (1 << 15) + lin(cells(5), 5)),
+                 ("octant, cell16, direction 16x32", (octant * 4096 + lin(cells(4), 4)) * 512 + dir9),
+                 ("cell128 (7 bits), octant", lin(cells(7), 7) * 8 + octant)):
+    run("secondary rays, sorted " + label, sec[np.argsort(k, kind="stable")])
 one = np.tile(sec[12345], N)
 run("one secondary ray repeated", one)
 # cost by hit type
