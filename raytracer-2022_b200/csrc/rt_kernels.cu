@@ -195,6 +195,7 @@ struct QueueIO {
         cur = idx;
     }
     /* pulls a queue entry that some warp will ask for a few microseconds from now into L2 */
+    __device__ __forceinline__ int refill_at() const { return perm ? RT_EXTEND_REFILL_SORTED : RT_EXTEND_REFILL; }
     __device__ __forceinline__ void prefetch(uint32_t idx) {
         if (!perm) asm volatile("prefetch.global.L2 [%0];" ::"l"(q.ray + idx));
     }
@@ -243,9 +244,12 @@ struct SortGrid {
     float lo[3], inv[3];
 };
 #ifndef RT_SORT_CELL_BITS
-#define RT_SORT_CELL_BITS 7
+#define RT_SORT_CELL_BITS 7 /* origin cells per axis = 2^bits */
 #endif
-constexpr int kSortKeyBits = 3 * RT_SORT_CELL_BITS + 3 + 8;
+#ifndef RT_SORT_DIR_BITS
+#define RT_SORT_DIR_BITS 8 /* direction below the octant: 8, 10, 12 = major axis + 2 x (3, 4, 5) bits, 6 = 2 x 3 bits, 0 = octant only */
+#endif
+constexpr int kSortKeyBits = 3 * RT_SORT_CELL_BITS + 3 + RT_SORT_DIR_BITS; /* radix passes = ceil(bits / 8) */
 __device__ __forceinline__ uint32_t spread_bits(uint32_t v) { /* RT_SORT_CELL_BITS bits -> every third bit */
     uint32_t r = 0;
 #pragma unroll
@@ -262,11 +266,15 @@ __device__ __forceinline__ uint32_t ray_sort_key(const SortGrid &g, V3 ro, V3 rd
     uint32_t oct = (d[0] < 0.f ? 1u : 0u) | (d[1] < 0.f ? 2u : 0u) | (d[2] < 0.f ? 4u : 0u);
     float ax = fabsf(d[0]), ay = fabsf(d[1]), az = fabsf(d[2]);
     float m = fmaxf(ax, fmaxf(ay, az));
-    float sc = m > 0.f ? 7.999f / m : 0.f;
+    constexpr int kFine = RT_SORT_DIR_BITS >= 8 ? (RT_SORT_DIR_BITS - 2) / 2 : 3; /* bits per minor direction component */
+    constexpr float kTop = (float)((1 << kFine) - 1);
+    float sc = m > 0.f ? (kTop + 0.999f) / m : 0.f;
     uint32_t major = (ax >= ay && ax >= az) ? 0u : (ay >= az ? 1u : 2u);
     float u = major == 0 ? ay : ax, v = major == 2 ? ay : az;
-    uint32_t dq = (major << 6) | ((uint32_t)fminf(u * sc, 7.f) << 3) | (uint32_t)fminf(v * sc, 7.f); /* 2 + 3 + 3 bits */
-    return (morton << 11) | (oct << 8) | dq;
+    uint32_t dq = 0;
+    if (RT_SORT_DIR_BITS >= 8) dq = (major << (2 * kFine)) | ((uint32_t)fminf(u * sc, kTop) << kFine) | (uint32_t)fminf(v * sc, kTop);
+    else if (RT_SORT_DIR_BITS == 6) dq = ((uint32_t)fminf(ax * sc, 7.f) << 3) | (uint32_t)fminf(ay * sc, 7.f);
+    return (((morton << 3) | oct) << RT_SORT_DIR_BITS) | dq;
 }
 /* moments of the first hit points of a wave (every 8th camera ray) */
 __global__ void k_sort_moments(PathQueue q, HitBuf hb, const uint32_t *count, double *moments /* sum xyz, sum xyz^2, n */) {
@@ -517,6 +525,7 @@ struct BatchIO {
         tmax = q.t_max;
         rng.init(keys ? keys[idx] : (uint64_t)idx, 0, 0, RT_DOMAIN_BATCH, 0);
     }
+    __device__ __forceinline__ int refill_at() const { return RT_EXTEND_REFILL; }
     __device__ __forceinline__ void prefetch(uint32_t idx) { asm volatile("prefetch.global.L2 [%0];" ::"l"(rays + idx)); }
     __device__ __forceinline__ double draw() { return rng.gen(); }
     __device__ __forceinline__ void store(uint32_t idx, const Closest &c) {
