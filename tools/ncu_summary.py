@@ -19,7 +19,9 @@ for r in rows[1:]:
         pass
     d[int(r[ii])]["name"] = r[ki]
 ids = sorted(d)
-half = len(ids) // 2  # first half = warm-up step, second half = the timed step
+# the timed step starts at the last k_raygen launch (one wave per step); everything before it is the warm-up step
+starts = [k for k, i in enumerate(ids) if "k_raygen" in d[i]["name"]]
+half = starts[-1] if starts else len(ids) // 2
 agg = defaultdict(lambda: [0, 0.0, 0.0, 0.0])
 seq = []
 for i in ids[half:]:
