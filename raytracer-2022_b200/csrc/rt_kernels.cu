@@ -879,8 +879,7 @@ rtgpu_status run_wave(rtgpu_scene *s, const WaveParams &wp, int max_depth, cudaS
                 size_t tb = s->sort_temp_bytes;
                 CK(cub::DeviceRadixSort::SortPairs(s->sort_temp, tb, s->sort_keys[0], s->sort_keys[1], s->sort_idx[0], s->sort_idx[1],
                                                    (int)nb, 0, kSortKeyBits, stream));
-                perm = s->sort_idx[1];
-                if (wt) wt->launches += 3;
+                perm = s->sort_idx[1]; /* (the library's sort kernels are not counted in stats->launches: those are this file's) */
             } else {
                 sorting = false; /* queues only shrink: the rest of the wave runs in arrival order */
             }
@@ -899,6 +898,7 @@ rtgpu_status run_wave(rtgpu_scene *s, const WaveParams &wp, int max_depth, cudaS
             CK(cudaMemsetAsync(s->sort_bounds, 0, 7 * sizeof(double), stream));
             k_sort_moments<<<blocks, kThreads, 0, stream>>>(qin, s->hb, s->counts + b, s->sort_bounds);
             k_sort_grid<<<1, 1, 0, stream>>>(s->sort_bounds, grid);
+            if (wt) wt->launches += 2;
         }
         {
             uint32_t *cc = s->class_count + 8 * b;
