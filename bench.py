@@ -167,9 +167,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3_final_scene_800x800", choices=sorted(WORKLOADS))
-    ap.add_argument("--spp", type=int, default=96,
-                    help="samples per pixel per step per GPU; one step is ONE wave (all its paths in flight at once): deep bounces of a "
-                         "larger wave launch with more rays, 96 spp = 61 M paths measured +10 %% over 24 spp")
+    ap.add_argument("--spp", type=int, default=192,
+                    help="samples per pixel per step per GPU; one step is ONE wave (all its paths in flight at once, 276 B each): a "
+                         "larger wave launches its deep bounces with more rays and its sorted rays are closer neighbours; measured "
+                         "1 421 / 1 571 / 1 669 / 1 738 Mrays/s at 48 / 96 / 192 / 384 spp (17 / 34 / 68 GB at 96 / 192 / 384)")
     ap.add_argument("--ref-spp", type=int, default=2, help="samples per pixel per step of the CPU reference arm")
     ap.add_argument("--depth", type=int, default=50)
     ap.add_argument("--seed", type=int, default=2022)

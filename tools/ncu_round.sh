@@ -5,7 +5,7 @@
 PROF="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
 mkdir -p gpurun_out
 timeout 300 $PROF > gpurun_out/plain.log 2>&1 && \
-timeout 1500 ncu --metrics gpu__time_duration.sum,smsp__thread_inst_executed_per_inst_executed.ratio,smsp__inst_executed.sum --clock-control none -c 1600 --csv --log-file gpurun_out/launches_full.csv $PROF > gpurun_out/ncu_launches.log 2>&1
+timeout 1500 ncu --metrics gpu__time_duration.sum,smsp__thread_inst_executed_per_inst_executed.ratio,smsp__inst_executed.sum --clock-control none -c 1700 --csv --log-file gpurun_out/launches_full.csv $PROF > gpurun_out/ncu_launches.log 2>&1
 timeout 300 $PROF > gpurun_out/plain2.log 2>&1 && \
 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_extend -s 51 -c 2 -o gpurun_out/prof_extend -f $PROF > gpurun_out/ncu_full.log 2>&1
 timeout 300 $PROF > gpurun_out/plain3.log 2>&1 && \

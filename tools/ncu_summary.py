@@ -37,7 +37,7 @@ for i in ids[half:]:
 tot = sum(a[1] for a in agg.values())
 with open(f"{out_dir}/{tag}_launches.txt", "w") as f:
     f.write("# ncu --metrics gpu__time_duration.sum,smsp__thread_inst_executed_per_inst_executed.ratio,smsp__inst_executed.sum --clock-control none\n")
-    f.write("# command: python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e   (C3 final_scene 800x800, one 96-spp wave per step)\n")
+    f.write("# command: python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e   (C3 final_scene 800x800, one wave per step: the bench default, see the bench line next to this file)\n")
     f.write("# per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.  Timed step only.\n")
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"{k:44s} launches {a[0]:4d}  time {a[1] / 1e6:8.2f} ms  share {a[1] / tot:.3f}  warp-instr {a[2] / 1e6:9.1f} M  "
@@ -93,7 +93,7 @@ if os.path.exists(f"{G}/prof_extend_deep.ncu-rep"):
         cols.append(("bounce 20", row, None))
 with open(f"{out_dir}/{tag}_k_extend_ncu.txt", "w") as f:
     f.write("# ncu --set full --clock-control none --import-source on -k regex:k_extend -s 51 -c 2   (and -s 70 -c 1 for the deep bounce)\n")
-    f.write("# launches of the timed step of: python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e  (one 96-spp wave)\n")
+    f.write("# launches of the timed step of: python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e  (one wave per step, bench default)\n")
     f.write("# columns: " + " | ".join(f"{n}" + (f" ({r / 1e6:.1f} M rays)" if r else "") for n, _, r in cols) + "\n")
     for w in want:
         if w in hdr:
