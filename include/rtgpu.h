@@ -172,7 +172,8 @@ typedef struct rtgpu_render_params {
     int32_t max_depth;          /* main.rs:39 */
     int32_t device;             /* CUDA device ordinal; -1 = current */
     uint64_t seed;
-    int64_t max_paths_in_flight; /* wave size cap; 0 = default */
+    int64_t max_paths_in_flight; /* wave size cap (276 B of device memory per path); 0 = a quarter of the free device memory,
+                                    between 2^24 and 2^27 paths */
     void *stream;                /* cudaStream_t; NULL = default stream */
     int32_t accumulate;          /* 0: overwrite accum, 1: add to it */
     int32_t accum_on_device;     /* 0: accum is host memory, 1: device memory */

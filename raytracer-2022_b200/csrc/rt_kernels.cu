@@ -1099,6 +1099,19 @@ rtgpu_status rtgpu_render(rtgpu_scene *s, const rtgpu_render_params *p, float *a
         return RTGPU_ERR_INVALID_ARG;
     }
     size_t max_paths = p->max_paths_in_flight > 0 ? (size_t)p->max_paths_in_flight : ((size_t)1 << 24);
+    if (p->max_paths_in_flight <= 0) {
+        /* default wave: larger waves are faster (deep bounces launch with more rays, sorted rays are closer neighbours), so a
+         * caller who does not say takes a quarter of the free device memory at 276 B per path, between 2^24 and 2^27 paths;
+         * the working memory this render already holds counts as free */
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            size_t paths = (free_b / 4 + s->cap * 276) / 276;
+            if (paths > ((size_t)1 << 27)) paths = (size_t)1 << 27;
+            if (paths > max_paths) max_paths = paths;
+        } else {
+            cudaGetLastError();
+        }
+    }
     if (max_paths < npix) max_paths = npix;
     if (max_paths > 0xfffffff0u) max_paths = 0xfffffff0u;
     int spp_per_wave = (int)(max_paths / npix);

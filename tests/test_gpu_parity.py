@@ -218,14 +218,14 @@ def test_per_sample_radiance(name):
     assert np.array_equal(np.isnan(g).any(axis=1), np.isnan(o).any(axis=1)) or (~finite).mean() < 0.01
 
 
-def test_wave_larger_than_the_default_cap_gives_the_same_image():
+def test_one_large_wave_and_several_small_ones_give_the_same_image():
     """bench.py renders ONE wave per step (max_paths_in_flight = all paths of the step): 1024x1024 x 20 spp = 21 M paths in one
-    wave (above the default cap of 16 Mi) against the default split into waves -- same rays, same image."""
+    wave against the same render split into waves of at most 16 Mi paths -- same rays, same image."""
     s, orc, gpu = get("cornell_box")
     w = h = 1024
     spp = 20
     a1, st1 = gpu.render(w, h, 0, spp, seed=9, max_paths_in_flight=w * h * spp)
-    a2, st2 = gpu.render(w, h, 0, spp, seed=9)
+    a2, st2 = gpu.render(w, h, 0, spp, seed=9, max_paths_in_flight=1 << 24)
     assert st1.rays == st2.rays and st1.samples == st2.samples == w * h * spp
     assert st1.launches < st2.launches  # one wave against two
     assert np.allclose(a1, a2, rtol=1e-6, atol=1e-6)
