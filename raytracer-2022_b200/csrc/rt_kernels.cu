@@ -3,17 +3,20 @@
  *
  * One wave = S samples of every pixel, all in flight at once (paths = S * W * H).  Per bounce:
  *
+ *   (sort)     bounces with enough rays are walked in the order of a 32-bit origin-cell / direction key that the
+ *              shade kernels wrote next to every ray; only (key, entry) pairs are sorted, the records stay put
  *   k_extend   closest hit of every live ray against the flat traversal program
  *              (BvhNode::hit, hittable/bvh/mod.rs:86-101, unrolled -- rt_device.cuh)
- *   k_shade    HitRecord of the winner, emitted/scatter/MixturePdf (ray_color, main.rs:233-278),
- *              survivors appended to the next queue with one warp-aggregated atomic
+ *   k_classify bins the hits by material class into index lists
+ *   k_shade<C> one kernel per class: HitRecord of the winner, emitted/scatter/MixturePdf (ray_color,
+ *              main.rs:233-278), survivors appended to the next queue with one warp-aggregated atomic
  *              (ballot + popc prefix) -- the compaction between bounces
  *
- * Path state lives in SoA queues of doubles (coalesced 8-byte lanes); the queue length stays on
- * the device (k_extend/k_shade of bounce b read counts[b], k_shade bumps counts[b+1]), so a
- * whole wave is enqueued without a host round trip.  Every path writes its radiance exactly
- * once, to contrib[path id], when it ends (miss / light / absorbed); k_accumulate then sums the
- * S samples of a pixel in a fixed order, which makes the image independent of scheduling.
+ * A queue entry is a 64-byte ray record plus a 32-byte state record; the queue length stays on the device
+ * (k_extend/k_shade of bounce b read counts[b], k_shade bumps counts[b+1]), so a wave is enqueued with one
+ * 4-byte readback per sorted bounce (the sort needs the length) or per 8 bounces.  Every path writes its
+ * radiance exactly once, to contrib[path id], when it ends (miss / light / absorbed); k_accumulate then sums the
+ * S samples of a pixel in a fixed order, which makes the image independent of scheduling and of the ray order.
  * Randomness: one Philox slot stream per path, keyed (seed, pixel, sample) -- include/rt_rng.h.
  */
 #include <cstdio>
