@@ -208,3 +208,21 @@ def test_native_driver_is_built_and_parses_arguments():
         pytest.skip("driver not built (no nccl.h on this machine)")
     r = subprocess.run([exe, "--bogus"], capture_output=True, text=True)
     assert r.returncode == 2 and "usage: rt_render" in r.stderr
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to the GPU arm) runs without a GPU and prints ONE JSON
+    line with the contract's keys; a tiny workload keeps it to a few seconds."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1_random_scene_400x225",
+                        "--ref-spp", "1", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "Mrays/s" and d["unit"] == "Mrays/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["config"]["workload"] == "c1_random_scene_400x225"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
