@@ -4,8 +4,13 @@
  * compiled with -fmad=false (rustc never contracts a*b+c), so hit/miss decisions and
  * primitive ids are bit-identical to BvhNode::hit (hittable/bvh/mod.rs:86-101).
  *
- * Layout of the scene in HBM: see include/rtgpu.h.  The traversal program is an array of
- * 64-byte ops; a thread fetches one op with four 128-bit loads through the read-only path.
+ * Layout of the scene in HBM: see include/rtgpu.h for what the caller hands over.  On the device the traversal
+ * program is re-packed into 32-byte UNITS (rtgpu_scene_create, rt_kernels.cu):
+ *     BvhNode   1 unit : kind | ordinal << 8, skip, f32 box (min.xyz, max.xyz); its f64 box lives in boxes64[ordinal]
+ *     any other 2 units: the caller's 64-byte op (two-slot ops: 4 units), skip re-mapped to units
+ * A thread fetches units i and i+1 with four 128-bit loads: a whole leaf op, or a BvhNode together with whatever
+ * follows it -- its left child, which is tested under the same fetch when it is a BvhNode too.  Boxes are decided
+ * by the f32 pre-test of rt_cull.h and, when that is not certain, by the f64 test on the f64 box.
  */
 #pragma once
 
@@ -15,8 +20,12 @@
 
 #include "../../include/rt_rng.h"
 #include "../../include/rtgpu.h"
+#include "rt_cull.h"
 
 #define RT_NO_HIT 0xffffffffu
+#ifndef RT_THREADS
+#define RT_THREADS 128 /* threads per block of the plain grid-stride kernels */
+#endif
 #define RT_MAX_PUSH 4   /* nesting of PUSH ops (instances inside instances) */
 #define RT_MAX_CHAIN 8  /* wrappers around one primitive */
 #define RT_PI 3.14159265358979323846264338327950288
@@ -48,7 +57,8 @@ __device__ __forceinline__ V3 ray_at(const Ray &r, double t) { return r.o + r.d 
 
 /* device view of a scene (pointers into HBM) */
 struct DScene {
-    const rtgpu_op *ops;
+    const uint4 *prog;      /* 32-byte units, two uint4 each */
+    const double2 *boxes64; /* f64 box of BvhNode `ordinal`: three double2 */
     const rtgpu_xform *xforms;
     const uint32_t *chain;
     const rtgpu_ctx *ctxs;
@@ -58,19 +68,21 @@ struct DScene {
     const rtgpu_image *images;
     const uint8_t *texels;
     const rtgpu_light *lights;
-    uint32_t n_ops, n_lights;
+    uint32_t n_units, n_lights;
+    float extent; /* largest |coordinate| of any BvhNode box (>= RT_CULL_MIN_EXTENT): the B of rt_cull.h */
     rtgpu_camera cam;
     double background[3];
 };
 
 /* ---- 128-bit loads of an op ------------------------------------------------------------- */
-__device__ __forceinline__ uint4 load_op_header(const rtgpu_op *op) { return __ldg(reinterpret_cast<const uint4 *>(op)); }
-__device__ __forceinline__ void load_op_payload(const rtgpu_op *op, double d[6]) {
+__device__ __forceinline__ const uint4 *unit_ptr(const uint4 *prog, uint32_t unit) { return prog + 2 * (size_t)unit; }
+__device__ __forceinline__ uint4 load_op_header(const uint4 *op) { return __ldg(op); }
+__device__ __forceinline__ void load_op_payload(const uint4 *op, double d[6]) {
     const double2 *p = reinterpret_cast<const double2 *>(op) + 1;
     double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
     d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y; d[4] = c.x; d[5] = c.y;
 }
-__device__ __forceinline__ void load_slot8(const rtgpu_op *op, double d[8]) { /* second slot of a 2-slot op */
+__device__ __forceinline__ void load_slot8(const uint4 *op, double d[8]) { /* second slot of a 2-slot op */
     const double2 *p = reinterpret_cast<const double2 *>(op);
     double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), e = __ldg(p + 3);
     d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y; d[4] = c.x; d[5] = c.y; d[6] = e.x; d[7] = e.y;
@@ -99,11 +111,13 @@ __device__ __forceinline__ void xform_ray(const rtgpu_xform &xf, V3 &o, V3 &d) {
 }
 /* the three arrays traversal needs, passed by value (kept in registers / the param bank) */
 struct TravScene {
-    const rtgpu_op *ops;
+    const uint4 *prog;
+    const double2 *boxes64;
     const rtgpu_xform *xforms;
     const uint32_t *chain;
+    float extent;
 };
-__device__ __forceinline__ TravScene trav_of(const DScene &sc) { return TravScene{sc.ops, sc.xforms, sc.chain}; }
+__device__ __forceinline__ TravScene trav_of(const DScene &sc) { return TravScene{sc.prog, sc.boxes64, sc.xforms, sc.chain, sc.extent}; }
 __device__ __forceinline__ rtgpu_xform load_xform(const TravScene &sc, uint32_t chain_idx) {
     const rtgpu_xform *x = sc.xforms + __ldg(sc.chain + chain_idx);
     const double2 *p = reinterpret_cast<const double2 *>(x);
@@ -212,33 +226,60 @@ __device__ __forceinline__ bool hit_aabb(V3 o, V3 inv, RaySigns sg, const double
     return !(tmax <= tmin);
 }
 
+static_assert(RT_MAX_PUSH >= 1, "push stack");
 /* ---- closest hit over a program range ------------------------------------------------------ */
 struct Closest {
     double t;      /* running best (= t_max when nothing was hit) */
-    uint32_t op;   /* index of the winning op, RT_NO_HIT if none */
+    uint32_t op;   /* unit index of the winning op, RT_NO_HIT if none */
     uint32_t face; /* box side of the winner */
 };
 
-/* Walks ops [begin, end) in order -- the reference's left-then-right recursion unrolled
- * (SURVEY.md 2.5).  The loop is "while-while": a tight run over consecutive NODE ops, then one
+/* Walks units [begin, end) in order -- the reference's left-then-right recursion unrolled
+ * (SURVEY.md 2.5).  The loop is "while-while": a tight run over consecutive NODE units, then one
  * leaf op, so that the lanes of a warp spend most iterations in the same code.
  * MAIN = false is the boundary walk of a ConstantMedium (no nested media, no rng).
- * `rng` draws the medium's free path (constantmedium.rs:60) in visiting order. */
-struct RayState {
-    V3 o, d, inv;
-    RaySigns sg;
-    __device__ __forceinline__ double a() const { return length_sqr(d); } /* |d|^2, recomputed where a sphere needs it */
+ * `rng` draws the medium's free path (constantmedium.rs:60) in visiting order.
+ *
+ * Where the f64 ray lives.  The NODE rounds only touch the f32 view (CullRay); origin, direction, shutter time
+ * and t_min in f64 are read by leaf tests and by the rare f64 box test.  The persistent warps of k_extend keep
+ * them in a per-thread column of shared memory (RaySmem), which frees 16 registers in the box loop; single-ray
+ * walks (medium boundaries) keep them in registers (RayRegs). */
+struct RayRegs {
+    V3 o_, d_;
+    double tm_, tmin_;
+    __device__ __forceinline__ V3 o() const { return o_; }
+    __device__ __forceinline__ V3 d() const { return d_; }
+    __device__ __forceinline__ double tm() const { return tm_; }
+    __device__ __forceinline__ double tmin() const { return tmin_; }
+    __device__ __forceinline__ void set_od(V3 o, V3 d) { o_ = o; d_ = d; }
+    __device__ __forceinline__ void set_times(double tm, double tmin) { tm_ = tm; tmin_ = tmin; }
 };
-__device__ __forceinline__ void ray_state_derive(RayState &r) {
-    r.inv = v3(1. / r.d.x, 1. / r.d.y, 1. / r.d.z);
-    r.sg.m = (r.inv.x < 0. ? 1u : 0u) | (r.inv.y < 0. ? 2u : 0u) | (r.inv.z < 0. ? 4u : 0u);
-}
+template <int STRIDE>
+struct RaySmem {
+    double *s; /* this thread's column: element k at s[k * STRIDE] (conflict-free: consecutive threads, consecutive doubles) */
+    __device__ __forceinline__ V3 o() const { return v3(s[0], s[STRIDE], s[2 * STRIDE]); }
+    __device__ __forceinline__ V3 d() const { return v3(s[3 * STRIDE], s[4 * STRIDE], s[5 * STRIDE]); }
+    __device__ __forceinline__ double tm() const { return s[6 * STRIDE]; }
+    __device__ __forceinline__ double tmin() const { return s[7 * STRIDE]; }
+    __device__ __forceinline__ void set_od(V3 o, V3 d) {
+        s[0] = o.x; s[STRIDE] = o.y; s[2 * STRIDE] = o.z;
+        s[3 * STRIDE] = d.x; s[4 * STRIDE] = d.y; s[5 * STRIDE] = d.z;
+    }
+    __device__ __forceinline__ void set_times(double tm, double tmin) { s[6 * STRIDE] = tm; s[7 * STRIDE] = tmin; }
+};
+#define RT_RAY_SLOT_DOUBLES 8
+#ifndef RT_RAY_IN_SMEM
+#define RT_RAY_IN_SMEM 1
+#endif
+#ifndef RT_NODE_PAIR
+#define RT_NODE_PAIR 1 /* test the NODE that follows a NODE under the same fetch */
+#endif
 
 __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm,
                                                      double tmin, double tmax);
 
 /* phases of the warp scheduler: ops whose code is the same run together */
-enum { PH_NODE = 0, PH_SPHERE = 1, PH_BOX = 2, PH_TRI = 3, PH_MISC = 4, PH_COUNT = 5, PH_NONE = 7 };
+enum { PH_NODE = 0, PH_SPHERE = 1, PH_BOX = 2, PH_TRI = 3, PH_MISC = 4, PH_EXACT = 5, PH_NONE = 7 };
 __device__ __forceinline__ uint32_t phase_of_kind(uint32_t kind) {
     /* NODE SPHERE MSPHERE RECT_XY RECT_XZ RECT_YZ BOX TRI MEDIUM PUSH POP RING, 3 bits each */
     return (uint32_t)((0444432444110ull >> (3 * kind)) & 7ull);
@@ -246,119 +287,193 @@ __device__ __forceinline__ uint32_t phase_of_kind(uint32_t kind) {
 
 struct SavedRays {
     double v[RT_MAX_PUSH][6];
+    float c[RT_MAX_PUSH][8]; /* the outer ray's CullRay: cheaper to keep than three divisions at the POP */
 };
 
-/* Resumable in-order walk of ops [begin, end).  The current op (header + payload, 64 B = four
- * 128-bit loads issued together) is fetched as soon as the index is known; exec_*() consume it.
+__device__ __forceinline__ float lo_f32(double x) { return __int_as_float(__double2loint(x)); }
+__device__ __forceinline__ float hi_f32(double x) { return __int_as_float(__double2hiint(x)); }
+
+/* Resumable in-order walk of units [begin, end).  Units i and i+1 (64 B = four 128-bit loads issued
+ * together) are fetched as soon as the index is known; exec_*() consume them.
  * One call of exec handles one op, so a warp can run "all lanes that sit on a NODE" together,
  * then "all lanes that sit on a sphere", ... (see extend_warp_loop). */
+template <typename RS>
 struct Traversal {
-    RayState r;
-    double tm, tmin;
+    RS ray;             /* f64 origin, direction, shutter time, t_min */
+    CullRay c;          /* f32 view for the box pre-test (rt_cull.h) */
+    float bestL, bestU; /* bestL <= best.t <= bestU */
     Closest best;
     uint32_t i, end;
     int sp;
-    uint4 h;     /* header of op i */
-    double p[6]; /* payload of op i */
+    bool unsure; /* the NODE at unit i could not be decided in f32: it waits for exec_node_exact */
+    uint4 h;     /* bytes 0..15 of unit i: header of a leaf op / kind|ordinal, skip, box min.xy of a NODE */
+    double p[6]; /* bytes 16..63: payload of a leaf op / rest of the NODE box, then unit i+1 */
     /* the PUSH/POP stack lives OUTSIDE this struct (SavedRays): it is indexed dynamically, and an
      * aggregate with a dynamically indexed member is kept in local memory as a whole */
 
-    /* header + payload are fetched together as soon as the index is known: the L1/L2 latency of the
-     * next op overlaps with the warp vote and with the other lanes' work */
+    /* fetched as soon as the index is known: the L1/L2 latency of the next op overlaps with the warp
+     * vote and with the other lanes' work */
     __device__ __forceinline__ void fetch_op(const TravScene sc) {
         if (i < end) {
-            const rtgpu_op *op = sc.ops + i;
+            const uint4 *op = unit_ptr(sc.prog, i);
             h = load_op_header(op);
             load_op_payload(op, p);
         }
+    }
+    __device__ __forceinline__ void set_best_bounds() {
+        bestL = rt_f32_down(best.t);
+        bestU = rt_f32_up(best.t);
+    }
+    __device__ __forceinline__ void derive(V3 o, V3 d, double tmin, float extent) {
+        /* 1/d: what AABB::hit divides per node (aabb.rs:17) */
+        cull_ray_setup(c, o.x, o.y, o.z, 1. / d.x, 1. / d.y, 1. / d.z, tmin, extent);
     }
     __device__ __forceinline__ void start(const TravScene sc, uint32_t begin, uint32_t end_, V3 o, V3 d, double tm_, double tmin_,
                                           double tmax) {
         best.t = tmax;
         best.op = RT_NO_HIT;
         best.face = 0;
-        r.o = o;
-        r.d = d;
-        ray_state_derive(r);
-        tm = tm_;
-        tmin = tmin_;
+        ray.set_od(o, d);
+        ray.set_times(tm_, tmin_);
+        derive(o, d, tmin_, sc.extent);
+        set_best_bounds();
         i = begin;
         end = end_;
         sp = 0;
+        unsure = false;
         fetch_op(sc);
     }
     __device__ __forceinline__ bool done() const { return i >= end; }
-    __device__ __forceinline__ uint32_t phase() const { return phase_of_kind(h.x & 0xffu); }
+    __device__ __forceinline__ uint32_t phase() const { return unsure ? (uint32_t)PH_EXACT : phase_of_kind(h.x & 0xffu); }
 
+    /* BvhNode::hit's box test (bvh/mod.rs:87) for the NODE at unit i and -- same fetch -- for the NODE that
+     * follows it, if any: that is its left child, tested next anyway when the first box is hit.  Both answers
+     * come from the f32 pre-test; a box it cannot decide is left for exec_node_exact (the lane changes phase,
+     * so the f64 code exists once, outside the NODE rounds). */
     __device__ __forceinline__ void exec_node(const TravScene sc) {
-        i = hit_aabb(r.o, r.inv, r.sg, p, tmin, best.t) ? i + 1 : h.y;
+        int ra = cull_box(c, __uint_as_float(h.z), __uint_as_float(h.w), lo_f32(p[0]), hi_f32(p[0]), lo_f32(p[1]), hi_f32(p[1]),
+                          bestL, bestU);
+        uint32_t bw = (uint32_t)__double2loint(p[2]), bskip = (uint32_t)__double2hiint(p[2]);
+        int rb = cull_box(c, lo_f32(p[3]), hi_f32(p[3]), lo_f32(p[4]), hi_f32(p[4]), lo_f32(p[5]), hi_f32(p[5]), bestL, bestU);
+        if (ra == RT_CULL_UNSURE) {
+            unsure = true;
+            return;
+        }
+        uint32_t nxt = i + 1; /* first box hit; what follows is a leaf, or a NODE the pre-test could not decide */
+        if (ra == RT_CULL_MISS) nxt = h.y;
+#if RT_NODE_PAIR
+        else if ((bw & 0xffu) == RTGPU_OP_NODE && rb != RT_CULL_UNSURE) nxt = rb == RT_CULL_MISS ? bskip : i + 2;
+#endif
+        i = nxt;
+        fetch_op(sc);
+    }
+    /* AABB::hit (aabb.rs:15-32) in f64 on the f64 box of the NODE at unit i */
+    __device__ __forceinline__ void exec_node_exact(const TravScene sc) {
+        const double2 *q = sc.boxes64 + 3 * (size_t)(h.x >> 8);
+        double2 b0 = __ldg(q), b1 = __ldg(q + 1), b2 = __ldg(q + 2);
+        double b[6] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y};
+        V3 d = ray.d();
+        V3 inv = v3(1. / d.x, 1. / d.y, 1. / d.z);
+        RaySigns sg;
+        sg.m = (inv.x < 0. ? 1u : 0u) | (inv.y < 0. ? 2u : 0u) | (inv.z < 0. ? 4u : 0u);
+        i = hit_aabb(ray.o(), inv, sg, b, ray.tmin(), best.t) ? i + 1 : h.y;
+        unsure = false;
         fetch_op(sc);
     }
     __device__ __forceinline__ void exec_sphere(const TravScene sc) {
-        V3 c = v3(p[0], p[1], p[2]);
-        uint32_t width = 1;
+        V3 c0 = v3(p[0], p[1], p[2]);
+        uint32_t width = 2;
         if ((h.x & 0xffu) == RTGPU_OP_MSPHERE) { /* MovingSphere::center, sphere.rs:124-127 */
             double q[8];
-            load_slot8(sc.ops + i + 1, q);
-            c = c + (v3(q[0], q[1], q[2]) - c) * ((tm - p[4]) / (p[5] - p[4]));
-            width = 2;
+            load_slot8(unit_ptr(sc.prog, i + 2), q);
+            c0 = c0 + (v3(q[0], q[1], q[2]) - c0) * ((ray.tm() - p[4]) / (p[5] - p[4]));
+            width = 4;
         }
-        if (hit_sphere(r.o, r.d, r.a(), c, p[3], tmin, best.t)) best.op = i;
+        V3 d = ray.d();
+        if (hit_sphere(ray.o(), d, length_sqr(d), c0, p[3], ray.tmin(), best.t)) {
+            best.op = i;
+            set_best_bounds();
+        }
         i += width;
         fetch_op(sc);
     }
     __device__ __forceinline__ void exec_box(const TravScene sc) {
-        if (hit_box(r.o, r.d, p, tmin, best.t, best.face)) best.op = i;
-        i += 1;
+        if (hit_box(ray.o(), ray.d(), p, ray.tmin(), best.t, best.face)) {
+            best.op = i;
+            set_best_bounds();
+        }
+        i += 2;
         fetch_op(sc);
     }
     __device__ __forceinline__ void exec_tri(const TravScene sc) {
         double q[8];
-        load_slot8(sc.ops + i + 1, q);
-        if (hit_triangle(r.o, r.d, v3(p[0], p[1], p[2]), v3(p[3], p[4], p[5]), v3(q[0], q[1], q[2]), v3(q[3], q[4], q[5]), tmin,
-                         best.t))
+        load_slot8(unit_ptr(sc.prog, i + 2), q);
+        if (hit_triangle(ray.o(), ray.d(), v3(p[0], p[1], p[2]), v3(p[3], p[4], p[5]), v3(q[0], q[1], q[2]), v3(q[3], q[4], q[5]),
+                         ray.tmin(), best.t)) {
             best.op = i;
-        i += 2;
+            set_best_bounds();
+        }
+        i += 4;
         fetch_op(sc);
     }
     /* rects, ConstantMedium, PUSH, POP.  DRAW() = next uniform of the ray's stream */
     template <bool MAIN, typename DRAW>
     __device__ __forceinline__ void exec_misc(const TravScene sc, SavedRays &stk, DRAW &&draw) {
-        switch (h.x & 0xffu) {
+        bool hit = false;
+        const uint32_t kind = h.x & 0xffu;
+        if (kind == RTGPU_OP_POP) {
+            --sp;
+            ray.set_od(v3(stk.v[sp][0], stk.v[sp][1], stk.v[sp][2]), v3(stk.v[sp][3], stk.v[sp][4], stk.v[sp][5]));
+            c.ix = stk.c[sp][0]; c.iy = stk.c[sp][1]; c.iz = stk.c[sp][2];
+            c.nx = stk.c[sp][3]; c.ny = stk.c[sp][4]; c.nz = stk.c[sp][5];
+            c.e2 = stk.c[sp][6]; c.tmin = stk.c[sp][7];
+            i += 2;
+            fetch_op(sc);
+            return;
+        }
+        V3 o = ray.o(), d = ray.d();
+        const double tmin = ray.tmin();
+        switch (kind) {
         case RTGPU_OP_RECT_XY:
-            if (hit_rect<2>(r.o, r.d, p[0], p[1], p[2], p[3], p[4], tmin, best.t)) best.op = i;
-            i += 1;
+            hit = hit_rect<2>(o, d, p[0], p[1], p[2], p[3], p[4], tmin, best.t);
+            if (hit) best.op = i;
+            i += 2;
             break;
         case RTGPU_OP_RECT_XZ:
-            if (hit_rect<1>(r.o, r.d, p[0], p[1], p[2], p[3], p[4], tmin, best.t)) best.op = i;
-            i += 1;
+            hit = hit_rect<1>(o, d, p[0], p[1], p[2], p[3], p[4], tmin, best.t);
+            if (hit) best.op = i;
+            i += 2;
             break;
         case RTGPU_OP_RECT_YZ:
-            if (hit_rect<0>(r.o, r.d, p[0], p[1], p[2], p[3], p[4], tmin, best.t)) best.op = i;
-            i += 1;
+            hit = hit_rect<0>(o, d, p[0], p[1], p[2], p[3], p[4], tmin, best.t);
+            if (hit) best.op = i;
+            i += 2;
             break;
         case RTGPU_OP_RING:
-            if (hit_ring(r.o, r.d, p[0], p[1], tmin, best.t)) best.op = i;
-            i += 1;
+            hit = hit_ring(o, d, p[0], p[1], tmin, best.t);
+            if (hit) best.op = i;
+            i += 2;
             break;
         case RTGPU_OP_MEDIUM:
             if constexpr (MAIN) { /* ConstantMedium::hit, constantmedium.rs:49-83 */
                 double t1 = CUDART_INF, t2 = CUDART_INF;
                 bool h1, h2 = false;
-                bool single_sphere = h.y == i + 2;
-                if (single_sphere) single_sphere = (load_op_header(sc.ops + i + 1).x & 0xffu) == RTGPU_OP_SPHERE;
+                const double a = length_sqr(d);
+                bool single_sphere = h.y == i + 4;
+                if (single_sphere) single_sphere = (load_op_header(unit_ptr(sc.prog, i + 2)).x & 0xffu) == RTGPU_OP_SPHERE;
                 if (single_sphere) { /* boundary = one Sphere (both media of final_scene) */
                     double bp[6];
-                    load_op_payload(sc.ops + i + 1, bp);
-                    V3 c = v3(bp[0], bp[1], bp[2]);
-                    h1 = hit_sphere(r.o, r.d, r.a(), c, bp[3], -CUDART_INF, t1);
-                    if (h1) h2 = hit_sphere(r.o, r.d, r.a(), c, bp[3], t1 + 0.0001, t2);
+                    load_op_payload(unit_ptr(sc.prog, i + 2), bp);
+                    V3 c0 = v3(bp[0], bp[1], bp[2]);
+                    h1 = hit_sphere(o, d, a, c0, bp[3], -CUDART_INF, t1);
+                    if (h1) h2 = hit_sphere(o, d, a, c0, bp[3], t1 + 0.0001, t2);
                 } else {
-                    Closest r1 = closest_hit_boundary(sc, i + 1, h.y, r.o, r.d, tm, -CUDART_INF, CUDART_INF);
+                    const double tm = ray.tm();
+                    Closest r1 = closest_hit_boundary(sc, i + 2, h.y, o, d, tm, -CUDART_INF, CUDART_INF);
                     h1 = r1.op != RT_NO_HIT;
                     t1 = r1.t;
                     if (h1) {
-                        Closest r2 = closest_hit_boundary(sc, i + 1, h.y, r.o, r.d, tm, t1 + 0.0001, CUDART_INF);
+                        Closest r2 = closest_hit_boundary(sc, i + 2, h.y, o, d, tm, t1 + 0.0001, CUDART_INF);
                         h2 = r2.op != RT_NO_HIT;
                         t2 = r2.t;
                     }
@@ -368,39 +483,38 @@ struct Traversal {
                     t2 = fmin(t2, best.t);
                     if (!(t1 >= t2)) {
                         t1 = fmax(t1, 0.);
-                        double ray_length = sqrt(r.a());
+                        double ray_length = sqrt(a);
                         double distance_inside_boundary = (t2 - t1) * ray_length;
                         double rnd = draw();
                         double hit_distance = p[0] * log(rnd); /* neg_inv_density * rnd.log(E) */
                         if (!(hit_distance > distance_inside_boundary)) {
                             best.t = t1 + hit_distance / ray_length;
                             best.op = i;
+                            hit = true;
                         }
                     }
                 }
             }
             i = h.y;
             break;
-        case RTGPU_OP_PUSH: {
-            stk.v[sp][0] = r.o.x; stk.v[sp][1] = r.o.y; stk.v[sp][2] = r.o.z;
-            stk.v[sp][3] = r.d.x; stk.v[sp][4] = r.d.y; stk.v[sp][5] = r.d.z;
+        default: { /* PUSH */
+            stk.v[sp][0] = o.x; stk.v[sp][1] = o.y; stk.v[sp][2] = o.z;
+            stk.v[sp][3] = d.x; stk.v[sp][4] = d.y; stk.v[sp][5] = d.z;
+            stk.c[sp][0] = c.ix; stk.c[sp][1] = c.iy; stk.c[sp][2] = c.iz;
+            stk.c[sp][3] = c.nx; stk.c[sp][4] = c.ny; stk.c[sp][5] = c.nz;
+            stk.c[sp][6] = c.e2; stk.c[sp][7] = c.tmin;
             ++sp;
             for (uint32_t j = 0; j < h.w; ++j) {
                 rtgpu_xform xf = load_xform(sc, h.z + j);
-                xform_ray(xf, r.o, r.d);
+                xform_ray(xf, o, d);
             }
-            ray_state_derive(r);
-            i += 1;
+            ray.set_od(o, d);
+            derive(o, d, tmin, sc.extent);
+            i += 2;
             break;
         }
-        default: /* POP */
-            --sp;
-            r.o = v3(stk.v[sp][0], stk.v[sp][1], stk.v[sp][2]);
-            r.d = v3(stk.v[sp][3], stk.v[sp][4], stk.v[sp][5]);
-            ray_state_derive(r);
-            i += 1;
-            break;
         }
+        if (hit) set_best_bounds();
         fetch_op(sc);
     }
     /* one op, whatever it is (single-ray loops) */
@@ -408,6 +522,7 @@ struct Traversal {
     __device__ __forceinline__ void step(const TravScene sc, SavedRays &stk, DRAW &&draw) {
         switch (phase()) {
         case PH_NODE: exec_node(sc); break;
+        case PH_EXACT: exec_node_exact(sc); break;
         case PH_SPHERE: exec_sphere(sc); break;
         case PH_BOX: exec_box(sc); break;
         case PH_TRI: exec_tri(sc); break;
@@ -419,7 +534,7 @@ struct Traversal {
 /* boundary walk of a medium whose boundary is not a single sphere: rare, kept out of line */
 __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm,
                                                      double tmin, double tmax) {
-    Traversal tr;
+    Traversal<RayRegs> tr;
     SavedRays stk;
     tr.start(sc, begin, end, o, d, tm, tmin, tmax);
     while (!tr.done()) tr.step<false>(sc, stk, []() { return 0.; });
@@ -430,9 +545,6 @@ __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_
 #define RT_EXTEND_REFILL 16 /* refill when at least this many lanes of the warp are idle (a refill stalls the whole warp on the
                                queue load, three reciprocals and the first op: 16 is 2.7 % faster than 8; 20+ loses lanes) */
 #endif
-#ifndef RT_MEDIUM_QUORUM
-#define RT_MEDIUM_QUORUM 8 /* lanes that must stand on a ConstantMedium before it runs (1 = no hold) */
-#endif
 #ifndef RT_PREFETCH_AHEAD
 #define RT_PREFETCH_AHEAD 16384 /* rays ahead of the fetch counter pulled into L2 at every refill (0 = off; +1 %) */
 #endif
@@ -441,42 +553,177 @@ __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_
                                       warp, so it pays to drain further (24: +1.7 % over 16, 8: -7 %, 32: -3 %) */
 #endif
 #ifndef RT_NODE_UNROLL
-#define RT_NODE_UNROLL 3 /* boxes a lane may test under one vote (A/B on the B200: 2 is +2..7 % over 1; 3 is +0.7 % over 2 on sorted rays) */
+#define RT_NODE_UNROLL 2 /* fetches a lane may consume under one vote; each tests one or two boxes (exec_node) */
 #endif
 #ifndef RT_NODE_QUORUM_PCT
 #define RT_NODE_QUORUM_PCT 35 /* keep running NODE rounds while at least this share of the live lanes sits on a NODE */
 #endif
 
-/* The extend loop of one warp (persistent): every lane owns one ray at a time.
- *  - dynamic fetch: a lane whose ray is finished takes the next ray index from a global counter
- *    (one atomic per refill of the warp), so trip-count differences do not idle lanes;
- *  - phase voting: each round the warp runs only the kind of op most lanes are waiting on
- *    (NODE / sphere / box / triangle / misc), so the instructions that are issued carry many
- *    active lanes instead of the 6-8 of 32 that plain SIMT divergence leaves.
- * Each ray still executes its own ops strictly in program order with its own running best, so
- * results are identical to the sequential walk.
- * IO: load(idx, o, d, tm, tmin, tmax), draw() -> next uniform of the current ray, store(idx, Closest). */
-#ifdef RT_DEBUG_COUNTERS
-/* [0] NODE rounds, [8] lanes that ran in them, [1..4] leaf ops by phase;  warp clocks: [16] refill/start, [17] NODE rounds,
- * [18] leaf section;  [20+ph] clocks the lanes of leaf phase ph spent in their case, [25+ph] how often that case ran */
-__device__ unsigned long long g_dbg[32];
+/* ---- the extend loop of one CTA: leaf tests are served warp-wide --------------------------------------------
+ * In extend_warp_loop a lane that reaches a leaf runs it in its own warp, one leaf kind after the other, with the
+ * 5 - 13 lanes that happen to sit on that kind: the leaf sections are about half of a warp's clocks for 6 of the
+ * ~31 ops of a ray.  Here the 16 warps of a CTA share per-kind REQUEST QUEUES in shared memory:
+ *
+ *   owner lane    owns one ray: its f32 view and the fetched op stay in registers, the f64 ray and the running best in
+ *                 its column of shared memory.  It walks NODE units (f32 pre-test), runs PUSH / POP / f64 box tests
+ *                 itself, and for every other op posts a request {its thread id} to the queue of that kind and waits.
+ *   any warp      whenever a queue holds 32 requests (or the warp has nothing else to do) it claims up to 32 of them
+ *                 and runs that ONE leaf kind for 32 different rays of the CTA -- uniform code, full lanes -- reading
+ *                 each requester's ray from shared memory and writing the new best and a done flag back.
+ *
+ * Each ray still meets its ops strictly in program order with its own running best (a ray has at most one request in
+ * flight and does not move until it is answered), so results are those of the sequential walk.
+ * IO: load(idx, o, d, tm, tmin, tmax, a, b, pos) -> the ray and the identity (a, b) / position of its random stream,
+ *     draw(a, b, pos) -> next uniform of that stream, store(Closest, pos), refill_at(), prefetch(idx). */
+#ifndef RT_CTA_THREADS
+#define RT_CTA_THREADS 512
 #endif
+#ifndef RT_SERVE_MIN
+#define RT_SERVE_MIN 32 /* requests a queue must hold before a warp that still has other work serves it */
+#endif
+#define RT_RING_SLOTS (2 * RT_CTA_THREADS)
+enum { SQ_SPHERE = 0, SQ_BOX = 1, SQ_TRI = 2, SQ_RECT = 3, SQ_MEDIUM = 4, SQ_COUNT = 5, SQ_LOCAL = 7 };
+__device__ __forceinline__ uint32_t service_queue_of_kind(uint32_t kind) {
+    /* NODE SPHERE MSPHERE RECT_XY RECT_XZ RECT_YZ BOX TRI MEDIUM PUSH POP RING, 3 bits each (7 = runs in the owner lane) */
+    return (uint32_t)((0377421333007ull >> (3 * kind)) & 7ull);
+}
+struct ServiceShared {
+    double ray[RT_RAY_SLOT_DOUBLES][RT_CTA_THREADS]; /* column T: o, d, shutter time, t_min of thread T's ray */
+    double best_t[RT_CTA_THREADS];
+    uint32_t req_unit[RT_CTA_THREADS]; /* unit index of the op thread T asks for */
+    uint32_t res[RT_CTA_THREADS];      /* answer: box face (0 for other kinds) on a hit, RT_NO_HIT on a miss */
+    uint32_t rng_a[RT_CTA_THREADS], rng_b[RT_CTA_THREADS], rng_pos[RT_CTA_THREADS];
+    uint32_t state[RT_CTA_THREADS]; /* 0 none, 1 request posted, 2 answered */
+    uint32_t head[8], tail[8];
+    /* entry of queue position P: (requester thread id + 1) | lap(P) << 10, lap(P) = (P / RT_RING_SLOTS) & 63: a reader of
+     * position P waits for that tag, so a slot that still holds an older lap (reserved, not written yet) is never mistaken */
+    uint16_t ring[SQ_COUNT][RT_RING_SLOTS];
+};
+__device__ __forceinline__ uint32_t ld_vol_u32(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ uint32_t ld_vol_u16(const uint16_t *p) { return *reinterpret_cast<const volatile uint16_t *>(p); }
+
+/* one request of queue `q` (warp-uniform) served by this lane for thread R of the CTA */
 template <typename IO>
-__device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_ops, uint32_t n, uint32_t *fetch, IO &io) {
-    const uint32_t lane = threadIdx.x & 31u;
-    Traversal tr;
+__device__ __forceinline__ void serve_leaf(const TravScene ts, ServiceShared &S, uint32_t q, uint32_t R, IO &io) {
+    const uint32_t u = S.req_unit[R];
+    const uint4 *op = unit_ptr(ts.prog, u);
+    const uint4 h = load_op_header(op);
+    double p[6];
+    load_op_payload(op, p);
+    const V3 o = v3(S.ray[0][R], S.ray[1][R], S.ray[2][R]), d = v3(S.ray[3][R], S.ray[4][R], S.ray[5][R]);
+    const double tmin = S.ray[7][R];
+    double best = S.best_t[R];
+    uint32_t face = 0;
+    bool hit = false;
+    const uint32_t kind = h.x & 0xffu;
+    if (q == SQ_SPHERE) {
+        V3 c0 = v3(p[0], p[1], p[2]);
+        if (kind == RTGPU_OP_MSPHERE) { /* MovingSphere::center, sphere.rs:124-127 */
+            double qq[8];
+            load_slot8(op + 4, qq);
+            c0 = c0 + (v3(qq[0], qq[1], qq[2]) - c0) * ((S.ray[6][R] - p[4]) / (p[5] - p[4]));
+        }
+        hit = hit_sphere(o, d, length_sqr(d), c0, p[3], tmin, best);
+    } else if (q == SQ_BOX) {
+        hit = hit_box(o, d, p, tmin, best, face);
+    } else if (q == SQ_TRI) {
+        double qq[8];
+        load_slot8(op + 4, qq);
+        hit = hit_triangle(o, d, v3(p[0], p[1], p[2]), v3(p[3], p[4], p[5]), v3(qq[0], qq[1], qq[2]), v3(qq[3], qq[4], qq[5]), tmin, best);
+    } else if (q == SQ_RECT) {
+        if (kind == RTGPU_OP_RECT_XY) hit = hit_rect<2>(o, d, p[0], p[1], p[2], p[3], p[4], tmin, best);
+        else if (kind == RTGPU_OP_RECT_XZ) hit = hit_rect<1>(o, d, p[0], p[1], p[2], p[3], p[4], tmin, best);
+        else if (kind == RTGPU_OP_RECT_YZ) hit = hit_rect<0>(o, d, p[0], p[1], p[2], p[3], p[4], tmin, best);
+        else hit = hit_ring(o, d, p[0], p[1], tmin, best);
+    } else { /* ConstantMedium::hit, constantmedium.rs:49-83 */
+        double t1 = CUDART_INF, t2 = CUDART_INF;
+        bool h1, h2 = false;
+        const double a = length_sqr(d);
+        bool single_sphere = h.y == u + 4;
+        if (single_sphere) single_sphere = (load_op_header(op + 4).x & 0xffu) == RTGPU_OP_SPHERE;
+        if (single_sphere) { /* boundary = one Sphere (both media of final_scene) */
+            double bp[6];
+            load_op_payload(op + 4, bp);
+            V3 c0 = v3(bp[0], bp[1], bp[2]);
+            h1 = hit_sphere(o, d, a, c0, bp[3], -CUDART_INF, t1);
+            if (h1) h2 = hit_sphere(o, d, a, c0, bp[3], t1 + 0.0001, t2);
+        } else {
+            const double tm = S.ray[6][R];
+            Closest r1 = closest_hit_boundary(ts, u + 2, h.y, o, d, tm, -CUDART_INF, CUDART_INF);
+            h1 = r1.op != RT_NO_HIT;
+            t1 = r1.t;
+            if (h1) {
+                Closest r2 = closest_hit_boundary(ts, u + 2, h.y, o, d, tm, t1 + 0.0001, CUDART_INF);
+                h2 = r2.op != RT_NO_HIT;
+                t2 = r2.t;
+            }
+        }
+        if (h1 && h2) {
+            t1 = fmax(t1, tmin);
+            t2 = fmin(t2, best);
+            if (!(t1 >= t2)) {
+                t1 = fmax(t1, 0.);
+                double ray_length = sqrt(a);
+                double distance_inside_boundary = (t2 - t1) * ray_length;
+                uint32_t pos = S.rng_pos[R];
+                double rnd = io.draw(S.rng_a[R], S.rng_b[R], pos);
+                S.rng_pos[R] = pos;
+                double hit_distance = p[0] * log(rnd); /* neg_inv_density * rnd.log(E) */
+                if (!(hit_distance > distance_inside_boundary)) {
+                    best = t1 + hit_distance / ray_length;
+                    hit = true;
+                }
+            }
+        }
+    }
+    if (hit) S.best_t[R] = best;
+    S.res[R] = hit ? face : RT_NO_HIT;
+    __threadfence_block();
+    *reinterpret_cast<volatile uint32_t *>(&S.state[R]) = 2u;
+}
+
+template <typename IO>
+__device__ __forceinline__ void extend_cta_loop(const TravScene ts, uint32_t n_units, uint32_t n, uint32_t *fetch, IO &io) {
+    extern __shared__ __align__(16) unsigned char rt_smem_raw[];
+    ServiceShared &S = *reinterpret_cast<ServiceShared *>(rt_smem_raw);
+    const uint32_t T = threadIdx.x, lane = T & 31u;
+    if (T < 8) {
+        S.head[T] = 0;
+        S.tail[T] = 0;
+    }
+    for (uint32_t k = T; k < SQ_COUNT * RT_RING_SLOTS; k += RT_CTA_THREADS) (&S.ring[0][0])[k] = 0;
+    S.state[T] = 0;
+    __syncthreads();
+
+    Traversal<RaySmem<RT_CTA_THREADS>> tr;
+    tr.ray.s = &S.ray[0][T];
     SavedRays stk;
-    bool active = false, exhausted = false;
-    uint32_t idx = 0;
+    bool active = false, waiting = false, exhausted = false;
     const int refill_at = io.refill_at();
-#ifdef RT_DEBUG_COUNTERS
-    unsigned long long dbg_acc[32]; /* per lane, flushed once at the end: atomics inside the loop would distort the clocks */
-    for (int k = 0; k < 32; ++k) dbg_acc[k] = 0;
-#endif
     for (;;) {
-#ifdef RT_DEBUG_COUNTERS
-        long long c0 = clock64();
-#endif
+        bool progress = false;
+        /* answers: a waiting lane picks up the new best and moves to its next op */
+        if (waiting && ld_vol_u32(&S.state[T]) == 2u) {
+            __threadfence_block();
+            const uint32_t r = S.res[T];
+            if (r != RT_NO_HIT) {
+                tr.best.t = S.best_t[T];
+                tr.best.op = tr.i;
+                tr.best.face = r;
+                tr.set_best_bounds();
+            }
+            const uint32_t kind = tr.h.x & 0xffu;
+            tr.i = kind == RTGPU_OP_MEDIUM ? tr.h.y : tr.i + ((kind == RTGPU_OP_MSPHERE || kind == RTGPU_OP_TRI) ? 4u : 2u);
+            tr.fetch_op(ts);
+            S.state[T] = 0;
+            waiting = false;
+            progress = true;
+            if (tr.done()) {
+                io.store(tr.best, S.rng_pos[T]);
+                active = false;
+            }
+        }
+        /* refill: idle lanes take the next rays of the global queue (one atomic per warp) */
         uint32_t idle = __ballot_sync(0xffffffffu, !active);
         if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= refill_at)) {
             int leader = __ffs(idle) - 1;
@@ -485,121 +732,137 @@ __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_
             base = __shfl_sync(0xffffffffu, base, leader);
             exhausted = base + (uint32_t)__popc(idle) >= n;
             if (!active) {
-                idx = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+                uint32_t idx = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
 #if RT_PREFETCH_AHEAD > 0
                 if (idx + RT_PREFETCH_AHEAD < n) io.prefetch(idx + RT_PREFETCH_AHEAD);
 #endif
                 if (idx < n) {
                     V3 o, d;
                     double tm, tmin, tmax;
-                    io.load(idx, o, d, tm, tmin, tmax);
-                    tr.start(ts, 0, n_ops, o, d, tm, tmin, tmax);
+                    uint32_t a, b, pos;
+                    io.load(idx, o, d, tm, tmin, tmax, a, b, pos);
+                    S.rng_a[T] = a;
+                    S.rng_b[T] = b;
+                    S.rng_pos[T] = pos;
+                    tr.start(ts, 0, n_units, o, d, tm, tmin, tmax);
                     active = !tr.done();
-                    if (!active) io.store(idx, tr.best);
+                    progress = true;
+                    if (!active) io.store(tr.best, pos);
                 }
             }
             idle = __ballot_sync(0xffffffffu, !active);
         }
-        if (idle == 0xffffffffu) break; /* no lane has a ray and none is left to fetch */
-        /* NODE rounds: as long as enough lanes sit on a BvhNode box, run only those (uniform code,
-         * one ballot of overhead); lanes that reached a leaf wait.  Then every waiting lane runs its
-         * leaf op once (plain SIMT over the few leaf kinds) and the cycle repeats. */
-        const uint32_t n_active = 32u - (uint32_t)__popc(idle);
-        const uint32_t node_quorum = max(1u, (n_active * RT_NODE_QUORUM_PCT) / 100u);
-        bool node_ran = false;
-#ifdef RT_DEBUG_COUNTERS
-        long long c1 = clock64();
-        if (lane == 0) dbg_acc[16] += (unsigned long long)(c1 - c0);
-#endif
+        if (idle == 0xffffffffu && exhausted) break; /* this warp is out of rays; requests of the others are served by the others */
+
+        /* NODE rounds: while enough of the runnable lanes sit on a BvhNode box only those run (uniform code) */
+        {
+            const uint32_t n_run = (uint32_t)__popc(__ballot_sync(0xffffffffu, active && !waiting));
+            const uint32_t node_quorum = max(1u, (n_run * RT_NODE_QUORUM_PCT) / 100u);
 #pragma unroll 1
-        for (;;) {
-            bool in_node = active && tr.phase() == PH_NODE;
-            uint32_t m = __ballot_sync(0xffffffffu, in_node);
-#ifdef RT_DEBUG_COUNTERS
-            if (lane == 0 && (uint32_t)__popc(m) >= node_quorum) {
-                dbg_acc[0] += 1ull;
-                dbg_acc[8] += (unsigned long long)__popc(m);
-            }
-#endif
-            if ((uint32_t)__popc(m) < node_quorum) break;
-            node_ran = true;
-            if (in_node) {
-                tr.exec_node(ts);
+            for (;;) {
+                bool in_node = active && !waiting && tr.phase() == PH_NODE;
+                uint32_t m = __ballot_sync(0xffffffffu, in_node);
+                if ((uint32_t)__popc(m) < node_quorum || n_run == 0u) break;
+                if (in_node) {
+                    progress = true;
+                    tr.exec_node(ts);
 #if RT_NODE_UNROLL >= 2
-                if (!tr.done() && tr.phase() == PH_NODE) tr.exec_node(ts); /* second box under the same vote */
+                    if (!tr.done() && tr.phase() == PH_NODE) tr.exec_node(ts);
 #endif
 #if RT_NODE_UNROLL >= 3
-                if (!tr.done() && tr.phase() == PH_NODE) tr.exec_node(ts);
+                    if (!tr.done() && tr.phase() == PH_NODE) tr.exec_node(ts);
 #endif
-                if (tr.done()) {
-                    io.store(idx, tr.best);
-                    active = false;
+                    if (tr.done()) {
+                        io.store(tr.best, S.rng_pos[T]);
+                        active = false;
+                    }
                 }
             }
         }
-        /* expensive leaves are held back until enough lanes want the same code: a ConstantMedium costs ~300
-         * instructions (two boundary hits, Philox, log) and every ray of a foggy scene meets it, so the
-         * lanes standing on one pile up quickly; they run together instead of 5 at a time. */
-        bool hold = false;
-#ifdef RT_DEBUG_COUNTERS
-        long long c2 = clock64();
-        if (lane == 0) dbg_acc[17] += (unsigned long long)(c2 - c1);
-#endif
-#if RT_MEDIUM_QUORUM > 1
-        {
-            bool at_medium = active && (tr.h.x & 0xffu) == RTGPU_OP_MEDIUM;
-            uint32_t mm = __ballot_sync(0xffffffffu, at_medium);
-            if (mm) {
-                /* hold only while something else certainly advances this iteration (a NODE round ran, or another
-                 * lane runs a different leaf below); lanes on a NODE under the node quorum do NOT count */
-                uint32_t other_leaf = __ballot_sync(0xffffffffu, active && !at_medium && tr.phase() != PH_NODE);
-                hold = at_medium && (uint32_t)__popc(mm) < (uint32_t)RT_MEDIUM_QUORUM && (node_ran || other_leaf != 0u);
+        /* ops the owner runs itself (f64 box test, PUSH, POP), then requests for everything else */
+        uint32_t want = SQ_LOCAL;
+        if (active && !waiting) {
+            const uint32_t ph = tr.phase();
+            if (ph == PH_EXACT) {
+                tr.exec_node_exact(ts);
+                progress = true;
+            } else if (ph != PH_NODE) {
+                want = service_queue_of_kind(tr.h.x & 0xffu);
+                if (want == SQ_LOCAL) {
+                    tr.template exec_misc<true>(ts, stk, []() { return 0.; }); /* PUSH / POP */
+                    progress = true;
+                }
             }
-        }
-#endif
-        if (active && !hold) {
-#ifdef RT_DEBUG_COUNTERS
-            dbg_acc[tr.phase()] += 1ull;
-#endif
-#ifdef RT_DEBUG_COUNTERS
-#define RT_TIMED(PH, CALL)                                                                             \
-    {                                                                                                  \
-        long long a_ = clock64();                                                                      \
-        CALL;                                                                                          \
-        long long b_ = clock64();                                                                      \
-        if ((int)lane == __ffs(__activemask()) - 1) { /* the lanes of this case have not reconverged yet */ \
-            dbg_acc[20 + PH] += (unsigned long long)(b_ - a_);                                         \
-            dbg_acc[25 + PH] += 1ull;                                                                  \
-        }                                                                                              \
-    }
-#else
-#define RT_TIMED(PH, CALL) CALL
-#endif
-            switch (tr.phase()) {
-            case PH_NODE: break; /* below the quorum: waits for the next NODE rounds */
-            case PH_SPHERE: RT_TIMED(PH_SPHERE, tr.exec_sphere(ts)); break;
-            case PH_BOX: RT_TIMED(PH_BOX, tr.exec_box(ts)); break;
-            case PH_TRI: RT_TIMED(PH_TRI, tr.exec_tri(ts)); break;
-            default: RT_TIMED(PH_MISC, tr.exec_misc<true>(ts, stk, [&]() { return io.draw(); })); break;
-            }
-#undef RT_TIMED
             if (tr.done()) {
-                io.store(idx, tr.best);
+                io.store(tr.best, S.rng_pos[T]);
                 active = false;
+                want = SQ_LOCAL;
             }
         }
-#ifdef RT_DEBUG_COUNTERS
-        {
-            __syncwarp();
-            long long c3 = clock64();
-            if (lane == 0) dbg_acc[18] += (unsigned long long)(c3 - c2);
+        if (__any_sync(0xffffffffu, want != SQ_LOCAL)) {
+            if (want != SQ_LOCAL) {
+                S.req_unit[T] = tr.i;
+                S.best_t[T] = tr.best.t;
+                *reinterpret_cast<volatile uint32_t *>(&S.state[T]) = 1u;
+                waiting = true;
+                progress = true;
+            }
+            __threadfence_block();
+#pragma unroll
+            for (uint32_t q = 0; q < SQ_COUNT; ++q) {
+                uint32_t m = __ballot_sync(0xffffffffu, want == q);
+                if (m) {
+                    int leader = __ffs(m) - 1;
+                    uint32_t base = 0;
+                    if ((int)lane == leader) base = atomicAdd(&S.tail[q], (uint32_t)__popc(m));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (want == q) {
+                        uint32_t pos = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                        *reinterpret_cast<volatile uint16_t *>(&S.ring[q][pos & (RT_RING_SLOTS - 1)]) =
+                            (uint16_t)((T + 1u) | (((pos / RT_RING_SLOTS) & 63u) << 10));
+                    }
+                }
+            }
         }
-#endif
+        /* service: lane q (< SQ_COUNT) looks at queue q; a full batch is always taken, anything at all when this warp is stalled */
+        {
+            uint32_t avail = 0;
+            if (lane < SQ_COUNT) avail = ld_vol_u32(&S.tail[lane]) - ld_vol_u32(&S.head[lane]);
+            const bool stalled = !__any_sync(0xffffffffu, progress);
+            uint32_t ready = __ballot_sync(0xffffffffu, avail >= (stalled ? 1u : (uint32_t)RT_SERVE_MIN));
+            if (ready) {
+                const uint32_t q = (uint32_t)(__ffs(ready) - 1);
+                uint32_t h0 = 0, cnt = 0;
+                if (lane == 0) {
+                    for (;;) {
+                        uint32_t hh = ld_vol_u32(&S.head[q]), tt = ld_vol_u32(&S.tail[q]);
+                        uint32_t av = tt - hh;
+                        if (av == 0u) break;
+                        uint32_t c = av < 32u ? av : 32u;
+                        if (atomicCAS(&S.head[q], hh, hh + c) == hh) {
+                            h0 = hh;
+                            cnt = c;
+                            break;
+                        }
+                    }
+                }
+                h0 = __shfl_sync(0xffffffffu, h0, 0);
+                cnt = __shfl_sync(0xffffffffu, cnt, 0);
+                if (lane < cnt) {
+                    const uint32_t pos = h0 + lane, tag = (pos / RT_RING_SLOTS) & 63u;
+                    uint32_t e;
+                    do {
+                        e = ld_vol_u16(&S.ring[q][pos & (RT_RING_SLOTS - 1)]);
+                    } while ((e >> 10) != tag || (e & 1023u) == 0u);
+                    __threadfence_block();
+                    serve_leaf(ts, S, q, (e & 1023u) - 1u, io);
+                }
+                __syncwarp();
+            } else if (stalled) {
+                __nanosleep(40);
+            }
+        }
     }
-#ifdef RT_DEBUG_COUNTERS
-    for (int k = 0; k < 32; ++k)
-        if (dbg_acc[k]) atomicAdd(&g_dbg[k], dbg_acc[k]);
-#endif
 }
 
 /* ---- HitRecord of the winner (hittable/mod.rs:18-57), rebuilt once per ray ------------------- */
@@ -637,7 +900,7 @@ __device__ __forceinline__ void rect_record(HitRec &rec, V3 o, V3 d, double a0, 
 /* WANT_UV = false skips the sphere's acos/atan2 (only an ImageTexture reads u, v of a sphere) */
 template <bool WANT_UV>
 __device__ __noinline__ void make_record(const DScene &sc, const Ray &wr, double t, uint32_t opi, uint32_t face, HitRec &rec) {
-    const rtgpu_op *op = sc.ops + opi;
+    const uint4 *op = unit_ptr(sc.prog, opi);
     uint4 h = load_op_header(op);
     uint32_t kind = h.x & 0xffu;
     double p[6];
@@ -662,7 +925,7 @@ __device__ __noinline__ void make_record(const DScene &sc, const Ray &wr, double
         V3 c = v3(p[0], p[1], p[2]);
         if (kind == RTGPU_OP_MSPHERE) {
             double q[8];
-            load_slot8(op + 1, q);
+            load_slot8(op + 4, q); /* second slot = units opi+2, opi+3 */
             c = c + (v3(q[0], q[1], q[2]) - c) * ((wr.tm - p[4]) / (p[5] - p[4]));
         }
         V3 at = o + d * t;
@@ -696,7 +959,7 @@ __device__ __noinline__ void make_record(const DScene &sc, const Ray &wr, double
         break;
     case RTGPU_OP_TRI: { /* triangle.rs:62-76 */
         double q[8];
-        load_slot8(op + 1, q);
+        load_slot8(op + 4, q); /* second slot = units opi+2, opi+3 */
         V3 a = v3(p[0], p[1], p[2]), b = v3(p[3], p[4], p[5]), c = v3(q[0], q[1], q[2]), n = v3(q[3], q[4], q[5]);
         V3 pt = o + d * t;
         double a1 = a.x - b.x, b1 = a.x - c.x, c1 = a.x - pt.x;

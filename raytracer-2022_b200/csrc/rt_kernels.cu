@@ -21,6 +21,7 @@
  */
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -184,8 +185,9 @@ struct QueueIO {
     HitBuf hb;
     WaveParams wp;
     const uint32_t *perm; /* sorted order -> queue entry (ray reordering without moving the records), or nullptr */
-    uint32_t pid, pos, cur;
-    __device__ __forceinline__ void load(uint32_t idx, V3 &o, V3 &d, double &tm, double &tmin, double &tmax) {
+    uint32_t cur;         /* queue entry of the ray this lane owns */
+    __device__ __forceinline__ void load(uint32_t idx, V3 &o, V3 &d, double &tm, double &tmin, double &tmax, uint32_t &a, uint32_t &b,
+                                         uint32_t &pos) {
         if (perm) idx = __ldg(perm + idx);
         RayRec rr = ld_ray_stream(q.ray + idx);
         o = v3(rr.ox, rr.oy, rr.oz);
@@ -193,23 +195,24 @@ struct QueueIO {
         tm = rr.tm;
         tmin = 0.001;
         tmax = RT_F64_MAX;
-        pid = rr.pid;
+        a = rr.pid; /* the path's Philox stream: (pixel, sample) follow from the path id */
+        b = 0;
         pos = rr.rng;
         cur = idx;
     }
-    /* pulls a queue entry that some warp will ask for a few microseconds from now into L2 */
     __device__ __forceinline__ int refill_at() const { return perm ? RT_EXTEND_REFILL_SORTED : RT_EXTEND_REFILL; }
+    /* pulls a queue entry that some warp will ask for a few microseconds from now into L2 */
     __device__ __forceinline__ void prefetch(uint32_t idx) {
         if (!perm) asm volatile("prefetch.global.L2 [%0];" ::"l"(q.ray + idx));
     }
-    __device__ __forceinline__ double draw() { /* the path's stream resumes at slot `pos` */
+    __device__ __forceinline__ double draw(uint32_t a, uint32_t, uint32_t &pos) const { /* the path's stream resumes at slot `pos` */
         rt_rng rng;
-        path_rng(rng, wp, pid, pos);
+        path_rng(rng, wp, a, pos);
         double u = rng.gen();
         pos = rng.pos;
         return u;
     }
-    __device__ __forceinline__ void store(uint32_t, const Closest &c) {
+    __device__ __forceinline__ void store(const Closest &c, uint32_t pos) {
         const uint32_t idx = cur;
 #if RT_STREAM_HINTS
         __stcs(hb.t + idx, c.t);
@@ -222,14 +225,14 @@ struct QueueIO {
 #endif
     }
 };
-__global__ void __launch_bounds__(kThreads, RT_EXTEND_MIN_BLOCKS) k_extend(DScene sc, PathQueue q, HitBuf hb, const uint32_t *count,
-                                                                           uint32_t *fetch, WaveParams wp, const uint32_t *perm) {
+__global__ void __launch_bounds__(RT_CTA_THREADS, 1) k_extend(DScene sc, PathQueue q, HitBuf hb, const uint32_t *count, uint32_t *fetch,
+                                                             WaveParams wp, const uint32_t *perm) {
     QueueIO io;
     io.q = q;
     io.hb = hb;
     io.wp = wp;
     io.perm = perm;
-    extend_warp_loop(trav_of(sc), sc.n_ops, *count, fetch, io);
+    extend_cta_loop(trav_of(sc), sc.n_units, *count, fetch, io);
 }
 
 /* ---- ray reordering between bounces ---------------------------------------------------------------
@@ -347,7 +350,7 @@ __global__ void __launch_bounds__(256) k_classify(DScene sc, const uint8_t *mat_
         if (i < n) {
             uint32_t hop = hb.op[i];
             cls = 0;
-            if (hop != RT_NO_HIT) cls = mat_class[load_op_header(sc.ops + (hop & 0x1fffffffu)).z];
+            if (hop != RT_NO_HIT) cls = mat_class[load_op_header(unit_ptr(sc.prog, hop & 0x1fffffffu)).z];
         }
         uint32_t peers = __match_any_sync(0xffffffffu, cls);
         if (cls != 0xffu) {
@@ -518,35 +521,45 @@ struct BatchIO {
     const uint64_t *keys;
     double *t;
     uint32_t *op, *rng_pos;
-    rt_rng rng;
-    __device__ __forceinline__ void load(uint32_t idx, V3 &o, V3 &d, double &tm, double &tmin, double &tmax) {
+    uint32_t cur;
+    __device__ __forceinline__ void load(uint32_t idx, V3 &o, V3 &d, double &tm, double &tmin, double &tmax, uint32_t &a, uint32_t &b,
+                                         uint32_t &pos) {
         rtgpu_ray q = rays[idx];
         o = v3(q.o[0], q.o[1], q.o[2]);
         d = v3(q.d[0], q.d[1], q.d[2]);
         tm = q.tm;
         tmin = q.t_min;
         tmax = q.t_max;
-        rng.init(keys ? keys[idx] : (uint64_t)idx, 0, 0, RT_DOMAIN_BATCH, 0);
+        uint64_t key = keys ? keys[idx] : (uint64_t)idx; /* stream BATCH(key) */
+        a = (uint32_t)key;
+        b = (uint32_t)(key >> 32);
+        pos = 0;
+        cur = idx;
     }
     __device__ __forceinline__ int refill_at() const { return RT_EXTEND_REFILL; }
     __device__ __forceinline__ void prefetch(uint32_t idx) { asm volatile("prefetch.global.L2 [%0];" ::"l"(rays + idx)); }
-    __device__ __forceinline__ double draw() { return rng.gen(); }
-    __device__ __forceinline__ void store(uint32_t idx, const Closest &c) {
-        t[idx] = c.t;
-        op[idx] = c.op == RT_NO_HIT ? RT_NO_HIT : (c.op | (c.face << 29));
-        rng_pos[idx] = rng.pos;
+    __device__ __forceinline__ double draw(uint32_t a, uint32_t b, uint32_t &pos) const {
+        rt_rng rng;
+        rng.init(((uint64_t)b << 32) | (uint64_t)a, 0, 0, RT_DOMAIN_BATCH, pos);
+        double u = rng.gen();
+        pos = rng.pos;
+        return u;
+    }
+    __device__ __forceinline__ void store(const Closest &c, uint32_t pos) {
+        t[cur] = c.t;
+        op[cur] = c.op == RT_NO_HIT ? RT_NO_HIT : (c.op | (c.face << 29));
+        rng_pos[cur] = pos;
     }
 };
-__global__ void __launch_bounds__(kThreads, RT_EXTEND_MIN_BLOCKS) k_trace_extend(DScene sc, const rtgpu_ray *rays, const uint64_t *keys,
-                                                                                 double *t, uint32_t *op, uint32_t *rng_pos, uint32_t n,
-                                                                                 uint32_t *fetch) {
+__global__ void __launch_bounds__(RT_CTA_THREADS, 1) k_trace_extend(DScene sc, const rtgpu_ray *rays, const uint64_t *keys, double *t,
+                                                                   uint32_t *op, uint32_t *rng_pos, uint32_t n, uint32_t *fetch) {
     BatchIO io;
     io.rays = rays;
     io.keys = keys;
     io.t = t;
     io.op = op;
     io.rng_pos = rng_pos;
-    extend_warp_loop(trav_of(sc), sc.n_ops, n, fetch, io);
+    extend_cta_loop(trav_of(sc), sc.n_units, n, fetch, io);
 }
 __global__ void __launch_bounds__(kThreads) k_trace_record(DScene sc, const rtgpu_ray *rays, const double *t, const uint32_t *op,
                                                            const uint32_t *rng_pos, rtgpu_hit *out, uint32_t n) {
@@ -697,7 +710,6 @@ rtgpu_status validate(const rtgpu_scene_desc *d) {
     };
     if (!d || !d->ops || d->n_ops == 0) return bad("empty traversal program (the reference panics on an empty BvhNode)");
     if (d->n_ops >= 0x1fffffffu) return bad("traversal program too long");
-    if (d->max_push_depth > RT_MAX_PUSH) return bad("wrapper nesting deeper than RT_MAX_PUSH");
     if (d->n_ctxs == 0) return bad("no contexts");
     for (uint32_t i = 0; i < d->n_ctxs; ++i) {
         if (d->ctxs[i].len > RT_MAX_CHAIN) return bad("more than RT_MAX_CHAIN wrappers around one primitive");
@@ -718,7 +730,9 @@ rtgpu_status validate(const rtgpu_scene_desc *d) {
             break;
         case RTGPU_OP_PUSH:
             if ((uint64_t)op.a + op.b > d->n_chain) return bad("PUSH chain out of range");
-            ++push;
+            if (op.skip <= i || op.skip > d->n_ops) return bad("skip index out of range");
+            /* the nesting is counted here, not taken from desc->max_push_depth: the walk saves one ray per level */
+            if (++push > RT_MAX_PUSH) return bad("wrapper nesting deeper than RT_MAX_PUSH");
             break;
         case RTGPU_OP_POP:
             if (--push < 0) return bad("POP without PUSH");
@@ -752,8 +766,68 @@ rtgpu_status validate(const rtgpu_scene_desc *d) {
             (uint64_t)im.offset + (uint64_t)im.width * (uint64_t)im.height * 3 > d->n_texel_bytes)
             return bad("image outside the texel buffer");
     }
-    for (uint32_t i = 0; i < d->n_lights; ++i)
-        if (d->lights[i].kind > RTGPU_LIGHT_DEAD) return bad("unknown light kind");
+    for (uint32_t i = 0; i < d->n_lights; ++i) {
+        const rtgpu_light &l = d->lights[i];
+        if (l.kind > RTGPU_LIGHT_DEAD) return bad("unknown light kind");
+        int np = l.kind == RTGPU_LIGHT_SPHERE ? 4 : (l.kind == RTGPU_LIGHT_DEAD ? 0 : 5);
+        for (int k = 0; k < np; ++k)
+            if (!(l.p[k] == l.p[k])) return bad("NaN light parameter");
+    }
+    return RTGPU_OK;
+}
+
+/* The caller's program (64-byte ops, include/rtgpu.h) -> the device's 32-byte units (rt_device.cuh): a BvhNode becomes
+ * ONE unit with an f32 copy of its box, its f64 box goes to boxes64[ordinal]; every other slot is copied as two units;
+ * skip indices are re-mapped.  Two zero units pad the end (the walk always fetches units i and i+1). */
+rtgpu_status repack_program(const rtgpu_scene_desc *d, std::vector<uint32_t> &units, std::vector<double> &boxes64, float *extent,
+                            uint32_t *n_units) {
+    std::vector<uint32_t> at((size_t)d->n_ops + 1);
+    uint32_t u = 0, n_nodes = 0;
+    for (uint32_t i = 0; i < d->n_ops;) {
+        uint32_t kind = d->ops[i].kind_ctx & 0xffu;
+        uint32_t width = (kind == RTGPU_OP_MSPHERE || kind == RTGPU_OP_TRI) ? 2 : 1;
+        for (uint32_t k = 0; k < width; ++k) at[i + k] = u + 2 * k;
+        if (kind == RTGPU_OP_NODE) {
+            u += 1;
+            ++n_nodes;
+        } else {
+            u += 2 * width;
+        }
+        i += width;
+    }
+    at[d->n_ops] = u;
+    if (u >= 0x1fffffffu || n_nodes >= (1u << 24)) {
+        g_err = "traversal program too long";
+        return RTGPU_ERR_INVALID_SCENE;
+    }
+    units.assign(((size_t)u + 2) * 8, 0u);
+    boxes64.assign((size_t)(n_nodes ? n_nodes : 1) * 6, 0.);
+    double ext = (double)RT_CULL_MIN_EXTENT;
+    uint32_t ordinal = 0;
+    for (uint32_t i = 0; i < d->n_ops;) {
+        const rtgpu_op &op = d->ops[i];
+        uint32_t kind = op.kind_ctx & 0xffu;
+        uint32_t width = (kind == RTGPU_OP_MSPHERE || kind == RTGPU_OP_TRI) ? 2 : 1;
+        uint32_t *w = units.data() + (size_t)at[i] * 8;
+        if (kind == RTGPU_OP_NODE) {
+            w[0] = RTGPU_OP_NODE | (ordinal << 8);
+            w[1] = at[op.skip];
+            for (int k = 0; k < 6; ++k) {
+                float f = (float)op.d[k]; /* nearest: rt_cull.h's bound assumes it */
+                memcpy(w + 2 + k, &f, 4);
+                boxes64[(size_t)ordinal * 6 + k] = op.d[k];
+                double a = op.d[k] < 0. ? -op.d[k] : op.d[k];
+                if (!(a <= ext)) ext = a; /* NaN or inf ends as an infinite extent: every box is then decided in f64 */
+            }
+            ++ordinal;
+        } else {
+            memcpy(w, &op, sizeof(rtgpu_op) * width);
+            if (kind == RTGPU_OP_MEDIUM || kind == RTGPU_OP_PUSH) w[1] = at[op.skip];
+        }
+        i += width;
+    }
+    *extent = (ext == ext && ext <= 3e38) ? nextafterf((float)ext, INFINITY) : INFINITY;
+    *n_units = u;
     return RTGPU_OK;
 }
 
@@ -775,6 +849,7 @@ rtgpu_status SceneArena::commit(rtgpu_scene *s) {
 }
 
 int grid_blocks() { return kSMs * kBlocksPerSM; }
+int extend_blocks() { return kSMs; } /* one persistent 512-thread CTA per SM (extend_cta_loop) */
 
 rtgpu_status ensure_wave(rtgpu_scene *s, size_t n_paths, int max_depth) {
     if (max_depth + 2 > s->max_counts) {
@@ -894,7 +969,7 @@ rtgpu_status run_wave(rtgpu_scene *s, const WaveParams &wp, int max_depth, cudaS
         }
         PathQueue &qin = s->q[cur], &qout = s->q[cur ^ 1];
         if (timing) CK(cudaEventRecord(s->events[ev++], stream));
-        k_extend<<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->counts + b, s->counts + s->max_counts + b, wp, perm);
+        k_extend<<<extend_blocks(), RT_CTA_THREADS, sizeof(ServiceShared), stream>>>(s->d, qin, s->hb, s->counts + b, s->counts + s->max_counts + b, wp, perm);
         CK(cudaGetLastError()); /* a failed extend launch must not let the shade kernels read stale hits */
         if (timing) CK(cudaEventRecord(s->events[ev++], stream));
         if (sorting && b == 0) { /* the origin grid of this wave's keys, from the first hit points */
@@ -1013,7 +1088,17 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
     if (const char *e = getenv("RTGPU_SORT_MIN")) s->sort_min = (uint32_t)atoll(e);
     memset(&s->d, 0, sizeof s->d);
     SceneArena arena;
-    arena.add(desc->ops, desc->n_ops, &s->d.ops);
+    std::vector<uint32_t> units;
+    std::vector<double> boxes64;
+    st = repack_program(desc, units, boxes64, &s->d.extent, &s->d.n_units);
+    if (st != RTGPU_OK) {
+        rtgpu_scene_destroy(s);
+        return st;
+    }
+    const float extent = s->d.extent;
+    const uint32_t n_units = s->d.n_units;
+    arena.add(reinterpret_cast<const uint4 *>(units.data()), units.size() / 4, &s->d.prog);
+    arena.add(reinterpret_cast<const double2 *>(boxes64.data()), boxes64.size() / 2, &s->d.boxes64);
     arena.add(desc->xforms, desc->n_xforms, &s->d.xforms);
     arena.add(desc->chain, desc->n_chain, &s->d.chain);
     arena.add(desc->ctxs, desc->n_ctxs, &s->d.ctxs);
@@ -1049,16 +1134,13 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
         rtgpu_scene_destroy(s);
         return st;
     }
-    s->d.n_ops = desc->n_ops;
+    s->d.n_units = n_units;
+    s->d.extent = extent;
     s->d.n_lights = desc->n_lights;
     s->d.cam = desc->camera;
     for (int c = 0; c < 3; ++c) s->d.background[c] = desc->background[c];
-    if (const char *e = getenv("RTGPU_L1_CARVEOUT")) { /* A/B: shared-memory carveout of the traversal kernels, percent */
-        int pct = atoi(e);
-        cudaFuncSetAttribute(k_extend, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(k_trace_extend, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaGetLastError();
-    }
+    CK(cudaFuncSetAttribute(k_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ServiceShared)));
+    CK(cudaFuncSetAttribute(k_trace_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ServiceShared)));
     *out = s;
     return RTGPU_OK;
 }
@@ -1216,7 +1298,7 @@ rtgpu_status rtgpu_trace_batch(rtgpu_scene *s, const rtgpu_ray *rays, int64_t n,
         CK(cudaEventCreate(&e0));
         CK(cudaEventCreate(&e1));
         CK(cudaEventRecord(e0, 0));
-        k_trace_extend<<<grid_blocks(), kThreads>>>(s->d, d_rays, d_keys, d_t, d_u32, d_u32 + n, (uint32_t)n, d_u32 + 2 * n);
+        k_trace_extend<<<extend_blocks(), RT_CTA_THREADS, sizeof(ServiceShared)>>>(s->d, d_rays, d_keys, d_t, d_u32, d_u32 + n, (uint32_t)n, d_u32 + 2 * n);
         CK(cudaEventRecord(e1, 0));
         k_trace_record<<<grid_blocks(), kThreads>>>(s->d, d_rays, d_t, d_u32, d_u32 + n, d_out, (uint32_t)n);
         CK(cudaGetLastError());

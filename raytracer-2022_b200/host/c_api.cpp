@@ -160,6 +160,25 @@ int rtg_build_config(rtg_scene *s, const char *name, double aspect_ratio, const 
     RTG_TRY(-1)
 }
 uint32_t rtg_rng_pos(const rtg_scene *s) { return s->sc.rng.pos; }
+/* include/rt_rng.h as the product compiles it (the same header the CUDA kernels include): one Philox4x32-10 block, and
+ * n slots / gen() / gen_range() / gen_index() draws of stream (seed; a, b, domain) from slot `start`.
+ * tests/test_rng.py pins them against the Random123 known-answer vectors and against rand 0.8.5's published recipes. */
+void rtg_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    rt_philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
+}
+void rtg_rng_stream(uint64_t seed, uint32_t a, uint32_t b, uint32_t domain, uint32_t start, int n, uint64_t *slots, double *gen,
+                    double *range_m1_1, uint32_t *index, uint32_t index_n) {
+    for (int pass = 0; pass < 4; ++pass) {
+        rt_rng r;
+        r.init(seed, a, b, domain, start);
+        for (int i = 0; i < n; ++i) {
+            if (pass == 0 && slots) slots[i] = r.next_u64();
+            if (pass == 1 && gen) gen[i] = r.gen();
+            if (pass == 2 && range_m1_1) range_m1_1[i] = r.gen_range(-1.0, 1.0);
+            if (pass == 3 && index) index[i] = r.gen_index(index_n);
+        }
+    }
+}
 int rtg_graph(const rtg_scene *s, rt_graph *out) {
     *out = s->sc.view();
     return 0;

@@ -7,7 +7,7 @@
  * stb_image-style kernel jpeg-decoder ports), JFIF YCbCr -> RGB, and libjpeg-style "fancy"
  * triangle upsampling for 2x chroma (h2v1 / h2v2), replication otherwise.  All assets under
  * source/ are baseline; earthmap.jpg is 4:4:4.  Rounding can differ from the crate by
- * +-1..2 LSB: parity unpinned, bounded by tests/test_assets.py against libjpeg-turbo (PIL).
+ * +-1..2 LSB: parity unpinned, bounded by tests/test_host_and_abi.py::test_jpeg_decoder_against_libjpeg / _420_ against libjpeg-turbo (PIL).
  */
 #include "rt_host.h"
 
@@ -314,6 +314,13 @@ bool decode_jpeg_mem(const uint8_t *data, size_t n, int &width, int &height, std
                 hmax = comps[c].h > hmax ? comps[c].h : hmax;
                 vmax = comps[c].v > vmax ? comps[c].v : vmax;
             }
+            /* the upsampler replicates by whole factors: a component whose factor does not divide the largest one
+             * (e.g. h = 3 beside h = 4) has planes narrower than the reads below assume */
+            for (int c = 0; c < nc; ++c)
+                if (hmax % comps[c].h != 0 || vmax % comps[c].v != 0) {
+                    err = "fractional chroma subsampling is not supported";
+                    return false;
+                }
             have_sof = true;
         } else if (m == 0xc2 || (m >= 0xc3 && m <= 0xcf && m != 0xc4 && m != 0xc8 && m != 0xcc)) {
             err = "progressive / lossless / arithmetic JPEG is not supported";
