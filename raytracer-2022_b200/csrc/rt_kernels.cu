@@ -185,9 +185,8 @@ struct QueueIO {
     HitBuf hb;
     WaveParams wp;
     const uint32_t *perm; /* sorted order -> queue entry (ray reordering without moving the records), or nullptr */
-    uint32_t cur;         /* queue entry of the ray this lane owns */
     __device__ __forceinline__ void load(uint32_t idx, V3 &o, V3 &d, double &tm, double &tmin, double &tmax, uint32_t &a, uint32_t &b,
-                                         uint32_t &pos) {
+                                         uint32_t &pos, uint32_t &cur) {
         if (perm) idx = __ldg(perm + idx);
         RayRec rr = ld_ray_stream(q.ray + idx);
         o = v3(rr.ox, rr.oy, rr.oz);
@@ -200,7 +199,6 @@ struct QueueIO {
         pos = rr.rng;
         cur = idx;
     }
-    __device__ __forceinline__ int refill_at() const { return perm ? RT_EXTEND_REFILL_SORTED : RT_EXTEND_REFILL; }
     /* pulls a queue entry that some warp will ask for a few microseconds from now into L2 */
     __device__ __forceinline__ void prefetch(uint32_t idx) {
         if (!perm) asm volatile("prefetch.global.L2 [%0];" ::"l"(q.ray + idx));
@@ -212,8 +210,7 @@ struct QueueIO {
         pos = rng.pos;
         return u;
     }
-    __device__ __forceinline__ void store(const Closest &c, uint32_t pos) {
-        const uint32_t idx = cur;
+    __device__ __forceinline__ void store(uint32_t idx, const Closest &c, uint32_t pos) {
 #if RT_STREAM_HINTS
         __stcs(hb.t + idx, c.t);
         __stcs(hb.op + idx, c.op == RT_NO_HIT ? RT_NO_HIT : (c.op | (c.face << 29)));
@@ -226,13 +223,13 @@ struct QueueIO {
     }
 };
 __global__ void __launch_bounds__(RT_CTA_THREADS, 1) k_extend(DScene sc, PathQueue q, HitBuf hb, const uint32_t *count, uint32_t *fetch,
-                                                             WaveParams wp, const uint32_t *perm) {
+                                                             WaveParams wp, const uint32_t *perm, PushSave *push_scratch) {
     QueueIO io;
     io.q = q;
     io.hb = hb;
     io.wp = wp;
     io.perm = perm;
-    extend_cta_loop(trav_of(sc), sc.n_units, *count, fetch, io);
+    extend_cta_loop(trav_of(sc), sc.n_units, *count, fetch, push_scratch, io);
 }
 
 /* ---- ray reordering between bounces ---------------------------------------------------------------
@@ -521,9 +518,8 @@ struct BatchIO {
     const uint64_t *keys;
     double *t;
     uint32_t *op, *rng_pos;
-    uint32_t cur;
     __device__ __forceinline__ void load(uint32_t idx, V3 &o, V3 &d, double &tm, double &tmin, double &tmax, uint32_t &a, uint32_t &b,
-                                         uint32_t &pos) {
+                                         uint32_t &pos, uint32_t &cur) {
         rtgpu_ray q = rays[idx];
         o = v3(q.o[0], q.o[1], q.o[2]);
         d = v3(q.d[0], q.d[1], q.d[2]);
@@ -536,7 +532,6 @@ struct BatchIO {
         pos = 0;
         cur = idx;
     }
-    __device__ __forceinline__ int refill_at() const { return RT_EXTEND_REFILL; }
     __device__ __forceinline__ void prefetch(uint32_t idx) { asm volatile("prefetch.global.L2 [%0];" ::"l"(rays + idx)); }
     __device__ __forceinline__ double draw(uint32_t a, uint32_t b, uint32_t &pos) const {
         rt_rng rng;
@@ -545,21 +540,22 @@ struct BatchIO {
         pos = rng.pos;
         return u;
     }
-    __device__ __forceinline__ void store(const Closest &c, uint32_t pos) {
+    __device__ __forceinline__ void store(uint32_t cur, const Closest &c, uint32_t pos) {
         t[cur] = c.t;
         op[cur] = c.op == RT_NO_HIT ? RT_NO_HIT : (c.op | (c.face << 29));
         rng_pos[cur] = pos;
     }
 };
 __global__ void __launch_bounds__(RT_CTA_THREADS, 1) k_trace_extend(DScene sc, const rtgpu_ray *rays, const uint64_t *keys, double *t,
-                                                                   uint32_t *op, uint32_t *rng_pos, uint32_t n, uint32_t *fetch) {
+                                                                   uint32_t *op, uint32_t *rng_pos, uint32_t n, uint32_t *fetch,
+                                                                   PushSave *push_scratch) {
     BatchIO io;
     io.rays = rays;
     io.keys = keys;
     io.t = t;
     io.op = op;
     io.rng_pos = rng_pos;
-    extend_cta_loop(trav_of(sc), sc.n_units, n, fetch, io);
+    extend_cta_loop(trav_of(sc), sc.n_units, n, fetch, push_scratch, io);
 }
 __global__ void __launch_bounds__(kThreads) k_trace_record(DScene sc, const rtgpu_ray *rays, const double *t, const uint32_t *op,
                                                            const uint32_t *rng_pos, rtgpu_hit *out, uint32_t n) {
@@ -649,6 +645,7 @@ struct WaveRes {
     int max_counts = 0;
     float *accum_dev = nullptr;
     size_t accum_cap = 0;
+    PushSave *push_scratch = nullptr; /* PUSH stacks of the extend kernel's pool slots: one per (CTA, slot, level) */
     std::vector<cudaEvent_t> events;
     /* ray reordering: keys written by the shade kernels, their sorted copy, iota and the sorted entry indices */
     uint32_t *sort_keys[2] = {nullptr, nullptr}, *sort_idx[2] = {nullptr, nullptr};
@@ -662,6 +659,7 @@ struct WaveRes {
         if (class_count) cudaFree(class_count);
         if (counts_host) cudaFreeHost(counts_host);
         if (accum_dev) cudaFree(accum_dev);
+        if (push_scratch) cudaFree(push_scratch);
         if (sort_temp) cudaFree(sort_temp);
         for (cudaEvent_t e : events) cudaEventDestroy(e);
         *this = WaveRes();
@@ -969,7 +967,7 @@ rtgpu_status run_wave(rtgpu_scene *s, const WaveParams &wp, int max_depth, cudaS
         }
         PathQueue &qin = s->q[cur], &qout = s->q[cur ^ 1];
         if (timing) CK(cudaEventRecord(s->events[ev++], stream));
-        k_extend<<<extend_blocks(), RT_CTA_THREADS, sizeof(ServiceShared), stream>>>(s->d, qin, s->hb, s->counts + b, s->counts + s->max_counts + b, wp, perm);
+        k_extend<<<extend_blocks(), RT_CTA_THREADS, sizeof(PoolShared), stream>>>(s->d, qin, s->hb, s->counts + b, s->counts + s->max_counts + b, wp, perm, s->push_scratch);
         CK(cudaGetLastError()); /* a failed extend launch must not let the shade kernels read stale hits */
         if (timing) CK(cudaEventRecord(s->events[ev++], stream));
         if (sorting && b == 0) { /* the origin grid of this wave's keys, from the first hit points */
@@ -1139,8 +1137,9 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
     s->d.n_lights = desc->n_lights;
     s->d.cam = desc->camera;
     for (int c = 0; c < 3; ++c) s->d.background[c] = desc->background[c];
-    CK(cudaFuncSetAttribute(k_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ServiceShared)));
-    CK(cudaFuncSetAttribute(k_trace_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ServiceShared)));
+    if (!s->push_scratch) CK(cudaMalloc(&s->push_scratch, sizeof(PushSave) * (size_t)extend_blocks() * RT_POOL_RAYS * RT_MAX_PUSH));
+    CK(cudaFuncSetAttribute(k_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoolShared)));
+    CK(cudaFuncSetAttribute(k_trace_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoolShared)));
     *out = s;
     return RTGPU_OK;
 }
@@ -1298,7 +1297,7 @@ rtgpu_status rtgpu_trace_batch(rtgpu_scene *s, const rtgpu_ray *rays, int64_t n,
         CK(cudaEventCreate(&e0));
         CK(cudaEventCreate(&e1));
         CK(cudaEventRecord(e0, 0));
-        k_trace_extend<<<extend_blocks(), RT_CTA_THREADS, sizeof(ServiceShared)>>>(s->d, d_rays, d_keys, d_t, d_u32, d_u32 + n, (uint32_t)n, d_u32 + 2 * n);
+        k_trace_extend<<<extend_blocks(), RT_CTA_THREADS, sizeof(PoolShared)>>>(s->d, d_rays, d_keys, d_t, d_u32, d_u32 + n, (uint32_t)n, d_u32 + 2 * n, s->push_scratch);
         CK(cudaEventRecord(e1, 0));
         k_trace_record<<<grid_blocks(), kThreads>>>(s->d, d_rays, d_t, d_u32, d_u32 + n, d_out, (uint32_t)n);
         CK(cudaGetLastError());
