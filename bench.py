@@ -5,10 +5,16 @@
 
 A "step" is one pass of the hot path over one batch: every pixel of the 800x800 book-2 final
 scene (BASELINE.json configs[2]; the configuration north_star's target is quoted on) at
-`--spp` samples per pixel, depth 50 -- one full wave of the wavefront tracer per GPU.  With N
-GPUs every rank renders its own `--spp` samples (disjoint global sample indices: weak scaling
-by spp) and the float accumulation buffers are summed on rank 0 with one NCCL
-reduce per step.
+`--spp` samples per pixel, depth 50, through a pool of `--pool` paths in flight (path
+regeneration).  With N GPUs every rank renders its own `--spp` samples (disjoint global sample
+indices: weak scaling by spp) and the float accumulation buffers are summed on
+rank 0 with one NCCL reduce per step.
+
+Besides the headline line the same JSON carries
+  workloads : the other single-GPU configs of BASELINE.json in full (C1 book-1 scene 400x225 x 100 spp,
+              C2 Cornell 600x600 x 1000 spp, C4 OBJ mesh in Cornell 600x600 x 1000 spp), N = 1 only;
+  c5        : config 5, the book-2 final scene at 3840x2160 with a FIXED total of `--c5-spp` samples per
+              pixel split over the ranks (strong scaling) and the 99.5 MB NCCL reduce timed on its own.
 
 value   : rays of all ranks / device time of K steps (CUDA events, max over ranks), scene resident.
 e2e     : the same through the C ABI with HOST buffers: rtgpu_scene_create from the host arrays
@@ -111,17 +117,34 @@ def oracle_scene(scene):
     return OracleScene(scene)
 
 
-def cpu_baseline(scene, w, h, depth, budget_s=12.0):
-    """The oracle (CPU restatement of the reference) on a bounded sample of the same workload."""
-    threads = os.cpu_count() or 1
+def cpu_baseline(scene, w, h, depth, budget_s=8.0):
+    """The oracle (CPU restatement of the reference) on a bounded sample of the same workload, at T = all host threads and
+    at T = 8, the THREAD_NUMBER the reference ships with (main.rs:40)."""
     orc = oracle_scene(scene)
-    _, st = orc.render(w, h, 0, 1, max_depth=depth, seed=1, threads=threads)  # calibration pass
-    spp = max(1, min(64, int(budget_s / max(st.seconds, 1e-3))))
-    _, st = orc.render(w, h, 1, 1 + spp, max_depth=depth, seed=1, threads=threads)
-    return {"value": st.rays / st.seconds / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
-            "sample": f"{w}x{h} x {spp} spp, depth {depth}, {threads} threads, {st.seconds:.1f} s; C++ restatement of the "
-                      f"reference (no Rust toolchain), render loop only",
-            "samples_per_s": st.samples / st.seconds}
+    nproc = os.cpu_count() or 1
+
+    def run(threads):
+        _, st = orc.render(w, h, 0, 1, max_depth=depth, seed=1, threads=threads)  # calibration pass
+        spp = max(1, min(64, int(budget_s / max(st.seconds, 1e-3))))
+        _, st = orc.render(w, h, 1, 1 + spp, max_depth=depth, seed=1, threads=threads)
+        return st, spp
+
+    st, spp = run(nproc)
+    out = {"value": st.rays / st.seconds / 1e6, "unit": "Mrays/s", "cores": nproc, "kind": "port",
+           "sample": f"{w}x{h} x {spp} spp, depth {depth}, {nproc} threads, {st.seconds:.1f} s; C++ restatement of the "
+                     f"reference (no Rust toolchain), render loop only",
+           "samples_per_s": st.samples / st.seconds}
+    if nproc != 8:
+        st8, spp8 = run(min(8, nproc))
+        out["at_reference_thread_count"] = {"value": st8.rays / st8.seconds / 1e6, "unit": "Mrays/s", "cores": min(8, nproc),
+                                            "sample": f"{w}x{h} x {spp8} spp, {st8.seconds:.1f} s; THREAD_NUMBER = 8 (main.rs:40)"}
+    return out
+
+
+def workload_config(args, scene_name, w, h):
+    """`config` of the JSON line: what is rendered.  The same keys and values in both arms; how each arm runs it (spp per
+    step, threads / GPUs, pool) is under `run`."""
+    return {"workload": args.workload, "scene": scene_name, "width": w, "height": h, "max_depth": args.depth, "seed": args.seed}
 
 
 def run_reference(args, scene_name, w, h):
@@ -149,8 +172,8 @@ def run_reference(args, scene_name, w, h):
         "impl": "reference", "metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "scene": scene_name, "width": w, "height": h, "spp_per_step": spp,
-                   "max_depth": args.depth, "seed": args.seed, "parallelism": f"{threads} host threads (scanline blocks, main.rs:93-162)"},
+        "config": workload_config(args, scene_name, w, h),
+        "run": {"spp_per_step": spp, "parallelism": f"{threads} host threads (scanline blocks, main.rs:93-162)"},
         "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": threads, "kind": "port",
                          "sample": f"{w}x{h} x {spp} spp per step, {args.steps} steps; C++ restatement of the reference (oracle/), "
                                    f"Rust toolchain unavailable"},
@@ -160,6 +183,85 @@ def run_reference(args, scene_name, w, h):
     print(json.dumps(line), flush=True)
 
 
+def run_workload(rt, torch, name, spp, args, device, reps=2):
+    """One of the single-GPU configs of BASELINE.json rendered IN FULL (its own resolution and spp, depth 50): Mrays/s from
+    CUDA events around rtgpu_render with the accumulation buffer on the device, best of `reps` after one warm-up render."""
+    scene_name, w, h = WORKLOADS[name]
+    scene = rt.Scene(seed=args.seed).build_config(scene_name, w / h)
+    gpu = rt.GpuScene(scene.lower(), device=device)
+    acc = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    gpu.render(w, h, 0, min(spp, 16), max_depth=args.depth, seed=args.seed, accum_ptr=acc.data_ptr(), stream=stream, max_paths_in_flight=args.pool)
+    best = None
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        _, st = gpu.render(w, h, 0, spp, max_depth=args.depth, seed=args.seed, accum_ptr=acc.data_ptr(), stream=stream,
+                           max_paths_in_flight=args.pool)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if best is None or ms < best[0]:
+            best = (ms, st)
+    ms, st = best
+    gpu.close()
+    return {"scene": scene_name, "width": w, "height": h, "spp": spp, "max_depth": args.depth, "value": st.rays / ms / 1e3, "unit": "Mrays/s",
+            "ms": ms, "rays": int(st.rays), "samples_per_s": st.samples / (ms * 1e-3), "iterations": int(st.launches_extend),
+            "kernel_ms": {"extend": st.ms_extend, "shade": st.ms_shade, "other": st.ms_other}}
+
+
+def run_c5(rt, torch, dist, mg, args, rank, world, local):
+    """Config 5: the book-2 final scene at 3840x2160, a FIXED total of --c5-spp samples per pixel split over the ranks
+    (strong scaling), one NCCL SUM-reduce of the 99.5 MB accumulation buffer to rank 0.  Timed on the device
+    between barriers, max over ranks; the reduce is also timed on its own."""
+    scene_name, w, h = WORKLOADS["c5_final_scene_3840x2160"]
+    scene = rt.Scene(seed=args.seed).build_config(scene_name, w / h)
+    gpu = rt.GpuScene(scene.lower(), device=local)
+    acc = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    total = max(args.c5_spp, world)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def frame(first):
+        b, e = mg.shard_range(first, first + total, rank, world)
+        _, st = gpu.render(w, h, b, e, max_depth=args.depth, seed=args.seed, accum_ptr=acc.data_ptr(), stream=stream,
+                           max_paths_in_flight=args.pool)
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        mg.reduce_to_root(acc, world)
+        r1.record()
+        return st, r0, r1
+
+    b, e = mg.shard_range(0, max(world, 8), rank, world)  # warm-up: one small frame (sizes the pool, warms NCCL)
+    gpu.render(w, h, b, e, max_depth=args.depth, seed=args.seed, accum_ptr=acc.data_ptr(), stream=stream, max_paths_in_flight=args.pool)
+    mg.reduce_to_root(acc, world)
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    st, r0, r1 = frame(1000)
+    e1.record()
+    sync()
+    ms, ms_red = e0.elapsed_time(e1), r0.elapsed_time(r1)
+    rays = int(st.rays)
+    if world > 1:
+        t = torch.tensor([ms, ms_red], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_red = t[0].item(), t[1].item()
+        n = torch.tensor([rays], device="cuda", dtype=torch.int64)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+        rays = int(n.item())
+    gpu.close()
+    return {"scene": scene_name, "width": w, "height": h, "total_spp": total, "spp_per_gpu": total / world, "n_gpus": world,
+            "scaling": "strong", "value": rays / ms / 1e3, "unit": "Mrays/s", "ms": ms, "rays": rays,
+            "reduce_bytes": 3 * w * h * 4, "reduce_ms": ms_red, "samples_per_s": w * h * total / (ms * 1e-3),
+            "note": "strong-scaling efficiency at N GPUs = ms(N=1) / (N * ms(N)) from the c5 records of the N=1 and N=N lines"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -167,10 +269,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3_final_scene_800x800", choices=sorted(WORKLOADS))
-    ap.add_argument("--spp", type=int, default=192,
-                    help="samples per pixel per step per GPU; one step is ONE wave (all its paths in flight at once, 276 B each): a "
-                         "larger wave launches its deep bounces with more rays and its sorted rays are closer neighbours; measured "
-                         "1 421 / 1 571 / 1 669 / 1 738 Mrays/s at 48 / 96 / 192 / 384 spp (17 / 34 / 68 GB at 96 / 192 / 384)")
+    ap.add_argument("--spp", type=int, default=192, help="samples per pixel per step per GPU")
+    ap.add_argument("--pool", type=int, default=0,
+                    help="paths kept in flight per GPU (248 B each); 0 = the library default of 12 Mi paths (3.1 GB).  Finished paths "
+                         "are replaced by new camera rays, so every launch carries a full queue whatever the step size")
+    ap.add_argument("--c5-spp", type=int, default=256, help="total samples per pixel of the config-5 (3840x2160) leg, split over the ranks")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the C1 / C2 / C4 / C5 legs")
     ap.add_argument("--ref-spp", type=int, default=2, help="samples per pixel per step of the CPU reference arm")
     ap.add_argument("--depth", type=int, default=50)
     ap.add_argument("--seed", type=int, default=2022)
@@ -182,8 +286,11 @@ def main():
         args.warmup = max(args.warmup, 0)
 
     import __graft_entry__ as ge
-    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+    import fcntl
+    with open(os.path.join(ROOT, ".build.lock"), "w") as lk:  # every rank builds under the lock: the first one compiles,
+        fcntl.flock(lk, fcntl.LOCK_EX)                      # the others find the libraries up to date and only import
         ge.build(verbose=False)
+        fcntl.flock(lk, fcntl.LOCK_UN)
 
     if args.impl == "reference":
         run_reference(args, scene_name, w, h)
@@ -215,7 +322,7 @@ def main():
     accum = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
     spp = args.spp
     step_no = [0]
-    wave_paths = [w * h * spp]  # one wave per step; halved if the device cannot hold its 276 B per path
+    pool = [args.pool]  # paths in flight; halved if the device cannot hold them
 
     def step(g=gpu):
         """one pass of the hot path: this rank's spp shard of the frame, then the reduce"""
@@ -223,7 +330,7 @@ def main():
         step_no[0] += 1
         b, e = mg.step_sample_range(i, rank, world, spp)
         _, st = g.render(w, h, b, e, max_depth=args.depth, seed=args.seed, accum_ptr=accum.data_ptr(), stream=stream,
-                         max_paths_in_flight=wave_paths[0])
+                         max_paths_in_flight=pool[0])
         mg.reduce_to_root(accum, world)
         return st
 
@@ -232,15 +339,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    while True:  # the first warm-up step also sizes the wave to the device, before anything is timed
+    while True:  # the first warm-up step also sizes the pool to the device, before anything is timed
         try:
-            step()
+            st_first = step()
             break
         except rt.RtError as e:
-            if "memory" not in str(e).lower() or wave_paths[0] <= w * h:
+            if "memory" not in str(e).lower() or (pool[0] and pool[0] <= (1 << 20)):
                 raise
-            wave_paths[0] = max(w * h, wave_paths[0] // 2)
-            print(f"bench: wave does not fit this device, retrying with {wave_paths[0]} paths in flight", file=sys.stderr)
+            pool[0] = max(1 << 20, (pool[0] or (12 << 20)) // 2)
+            print(f"bench: pool does not fit this device, retrying with {pool[0]} paths in flight", file=sys.stderr)
     for _ in range(args.warmup - 1):
         step()
     # ---- timed region: K steps, scene resident in HBM ----
@@ -300,6 +407,17 @@ def main():
         e_ms = max(f0.elapsed_time(f1), e_wall)  # host work (scene_create) is part of the call
         e2e = (e_rays, e_ms, h2d, d2h, k_e2e)
 
+    # ---- the other configs of BASELINE.json (after the headline measurement; never inside its timed region) ----
+    gpu.close()
+    del accum
+    workloads, c5 = None, None
+    if not args.no_workloads:
+        if world == 1:
+            workloads = {}
+            for name, wl_spp in (("c1_random_scene_400x225", 100), ("c2_cornell_box_600x600", 1000), ("c4_obj_cornell_600x600", 1000)):
+                workloads[name] = run_workload(rt, torch, name, wl_spp, args, local)
+        c5 = run_c5(rt, torch, dist, mg, args, rank, world, local)
+
     # ---- max over ranks, totals ----
     if world > 1:
         t = torch.tensor([ms, e2e[1] if e2e else 0.0], device="cuda", dtype=torch.float64)
@@ -329,11 +447,11 @@ def main():
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "scene": scene_name, "width": w, "height": h, "spp_per_step_per_gpu": spp,
-                       "max_depth": args.depth, "seed": args.seed, "parallelism": f"spp-sharded x{world}, 1 NCCL reduce/step",
-                       "paths_in_flight_per_gpu": wave_paths[0],
-                       "wave_state_bytes_per_gpu": wave_paths[0] * 276,
-                       "l2": "wave state (276 B x paths = GBs per step) exceeds the 126 MB L2; scene arrays are L2-resident by design"},
+            "config": workload_config(args, scene_name, w, h),
+            "run": {"spp_per_step": spp, "parallelism": f"spp-sharded x{world}, 1 NCCL reduce/step",
+                    "paths_in_flight_per_gpu": int(st_first.pool_paths), "wave_state_bytes_per_gpu": int(st_first.pool_bytes),
+                    "iterations_per_step": launches_extend / max(args.steps, 1),
+                    "l2": "pool state (248 B x paths = GBs) exceeds the 126 MB L2; scene arrays are L2-resident by design"},
             "samples_per_s": samples_all / (ms * 1e-3),
             "rays_per_sample": rays_all / max(samples_all, 1),
             "clocks": clocks,
@@ -355,6 +473,10 @@ def main():
         if e2e:
             line["e2e"] = {"value": e_rays_all / e_ms_max / 1e3, "unit": "Mrays/s", "h2d_bytes_per_step": e2e[2],
                            "d2h_bytes_per_step": e2e[3], "steps": e2e[4], "ms_per_step": e_ms_max / e2e[4]}
+        if workloads:
+            line["workloads"] = workloads
+        if c5:
+            line["c5"] = c5
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(scene, w, h, args.depth)
         print(json.dumps(line), flush=True)

@@ -36,7 +36,8 @@ typedef enum rtgpu_status {
     RTGPU_ERR_INVALID_SCENE = 1, /* the reference would panic: empty BVH, missing box, bad index */
     RTGPU_ERR_INVALID_ARG = 2,
     RTGPU_ERR_CUDA = 3,
-    RTGPU_ERR_OOM = 4
+    RTGPU_ERR_OOM = 4,
+    RTGPU_ERR_NCCL = 5
 } rtgpu_status;
 
 /* ------------------------------------------------------------------------------------------
@@ -172,8 +173,8 @@ typedef struct rtgpu_render_params {
     int32_t max_depth;          /* main.rs:39 */
     int32_t device;             /* CUDA device ordinal; -1 = current */
     uint64_t seed;
-    int64_t max_paths_in_flight; /* wave size cap (276 B of device memory per path); 0 = a quarter of the free device memory,
-                                    between 2^24 and 2^27 paths */
+    int64_t max_paths_in_flight; /* size of the path pool (248 B of device memory per path); 0 = 12 Mi paths (3.1 GB).  Paths
+                                    that end are replaced by new camera rays while samples remain (path regeneration). */
     void *stream;                /* cudaStream_t; NULL = default stream */
     int32_t accumulate;          /* 0: overwrite accum, 1: add to it */
     int32_t accum_on_device;     /* 0: accum is host memory, 1: device memory */
@@ -188,8 +189,10 @@ typedef struct rtgpu_stats {
     double ms_shade;  /* summed duration of the shade kernel launches */
     double ms_other;  /* ray generation + accumulation */
     uint64_t launches;
-    uint64_t launches_extend;
+    uint64_t launches_extend; /* = iterations of the path pool */
     uint64_t rays_per_bounce[RTGPU_MAX_BOUNCE_STATS];
+    uint64_t pool_paths; /* paths the pool holds (the most that are in flight at once) */
+    uint64_t pool_bytes; /* device memory of the pool and of the pixel sums */
 } rtgpu_stats;
 
 const char *rtgpu_last_error(void);
@@ -220,6 +223,15 @@ rtgpu_status rtgpu_camera_rays(rtgpu_scene *scene, int32_t width, int32_t height
 rtgpu_status rtgpu_sample_radiance(rtgpu_scene *scene, int32_t width, int32_t height, int64_t first_pixel,
                                    int64_t n, int32_t k, int32_t max_depth, uint64_t seed, double *out_rgb,
                                    uint32_t *out_rays);
+
+/* The frame of main.rs:109-183 on several GPUs of one box: device g of G renders ALL pixels for the sample indices
+ * [spp_begin + g*n/G, spp_begin + (g+1)*n/G) (one host thread per device, where upstream has one per scanline block),
+ * then ONE ncclReduce(sum, float32, 3*width*height) brings the per-device sums to devices[0] and from there to the host
+ * buffer accum_root.  The scene is created on every device from `desc` and destroyed again.  devices == NULL means
+ * 0 .. n_devices-1.  params->stream / accumulate / accum_on_device must be 0.  stats are summed over the devices
+ * (ms_total: the slowest one); *ms_reduce is the wall time of the reduce.  NCCL is loaded at run time (libnccl.so.2). */
+rtgpu_status rtgpu_multi_render(const rtgpu_scene_desc *desc, const rtgpu_render_params *params, int32_t n_devices,
+                                const int32_t *devices, float *accum_root, rtgpu_stats *stats, double *ms_reduce);
 
 /* write_color (main.rs:280-299) on every pixel + the row flip of main.rs:197: rgb8 is
  * width*height*3 bytes, top row first.  accum may be host or device memory. */

@@ -72,7 +72,7 @@ def host_lib():
 
 GPU_SYMBOLS = [
     "rtgpu_last_error", "rtgpu_device_count", "rtgpu_scene_create", "rtgpu_scene_destroy", "rtgpu_render",
-    "rtgpu_trace_batch", "rtgpu_camera_rays", "rtgpu_sample_radiance", "rtgpu_resolve",
+    "rtgpu_trace_batch", "rtgpu_camera_rays", "rtgpu_sample_radiance", "rtgpu_resolve", "rtgpu_multi_render",
 ]
 
 
@@ -93,6 +93,9 @@ def gpu_lib():
         L.rtgpu_sample_radiance.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                             C.c_uint64, C.c_void_p, C.c_void_p]
         L.rtgpu_resolve.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        if hasattr(L, "rtgpu_multi_render"):  # (A/B builds of rt_kernels.cu alone, selected with RTGPU_LIB_PATH, may predate it)
+            L.rtgpu_multi_render.argtypes = [C.POINTER(D.rtgpu_scene_desc), C.POINTER(D.rtgpu_render_params), C.c_int32, C.c_void_p,
+                                             C.c_void_p, C.POINTER(D.rtgpu_stats), C.POINTER(C.c_double)]
         _gpu = L
     return _gpu
 
@@ -388,6 +391,27 @@ class GpuScene:
             st = self.G.rtgpu_resolve(C.c_void_p(accum.ctypes.data), width, height, spp, 0, C.c_void_p(out.ctypes.data))
         self._chk(st, "rtgpu_resolve")
         return out
+
+
+def multi_render(lowered, width, height, spp_begin, spp_end, n_devices, devices=None, max_depth=50, seed=2022, max_paths_in_flight=0):
+    """rtgpu_multi_render: the frame spp-sharded over `n_devices` GPUs of this box in ONE process, one NCCL reduce to the first.
+    Returns (accum float32 H x W x 3 on the host, stats summed over the devices, ms of the reduce)."""
+    G = gpu_lib()
+    p = D.rtgpu_render_params()
+    p.width, p.height, p.spp_begin, p.spp_end = width, height, spp_begin, spp_end
+    p.max_depth, p.device, p.seed = max_depth, -1, seed
+    p.max_paths_in_flight = max_paths_in_flight
+    accum = np.zeros((height, width, 3), dtype=np.float32)
+    stats = D.rtgpu_stats()
+    ms = C.c_double()
+    dv = None
+    if devices is not None:
+        arr = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        dv = C.cast(arr, C.c_void_p)
+    st = G.rtgpu_multi_render(C.byref(lowered.desc), C.byref(p), n_devices, dv, C.c_void_p(accum.ctypes.data), C.byref(stats), C.byref(ms))
+    if st != D.RTGPU_OK:
+        raise RtError(f"rtgpu_multi_render: status {st}: {(G.rtgpu_last_error() or b'').decode()}")
+    return accum, stats, ms.value
 
 
 def decode_jpeg(path):

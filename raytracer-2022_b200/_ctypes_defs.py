@@ -149,6 +149,7 @@ class rtgpu_stats(C.Structure):
         ("ms_total", C.c_double), ("ms_extend", C.c_double), ("ms_shade", C.c_double), ("ms_other", C.c_double),
         ("launches", C.c_uint64), ("launches_extend", C.c_uint64),
         ("rays_per_bounce", C.c_uint64 * RTGPU_MAX_BOUNCE_STATS),
+        ("pool_paths", C.c_uint64), ("pool_bytes", C.c_uint64),
     ]
 
 

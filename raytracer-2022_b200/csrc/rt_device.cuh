@@ -253,8 +253,13 @@ struct RayRegs {
     __device__ __forceinline__ void set_od(V3 o, V3 d) { o_ = o; d_ = d; }
     __device__ __forceinline__ void set_times(double tm, double tmin) { tm_ = tm; tmin_ = tmin; }
 };
+#ifndef RT_NODE_FETCH32
+#define RT_NODE_FETCH32 0 /* 1: fetch 32 bytes for a NODE and the other 32 only for leaf ops -- fewer L1 data-pipe cycles (50 % -> 35 %)
+                             but the dependent second fetch lengthens every leaf: 8 % slower on the B200 */
+#endif
 #ifndef RT_NODE_PAIR
-#define RT_NODE_PAIR 1 /* test the NODE that follows a NODE under the same fetch */
+#define RT_NODE_PAIR 0 /* with 64-byte fetches: also test the NODE that follows a NODE under the same fetch (2 % slower: the
+                          second test is wasted whenever the first box is missed) */
 #endif
 
 __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm,
@@ -299,7 +304,20 @@ struct Traversal {
         if (i < end) {
             const uint4 *op = unit_ptr(sc.prog, i);
             h = load_op_header(op);
-            load_op_payload(op, p);
+            const double2 *q = reinterpret_cast<const double2 *>(op) + 1;
+            double2 a = __ldg(q);
+            p[0] = a.x;
+            p[1] = a.y;
+#if RT_NODE_FETCH32
+            /* a NODE is one 32-byte unit: two 128-bit loads.  Only a leaf op needs units i and i+1; its second half is
+             * asked for once the kind is known (every 128-bit load of a warp costs four L1 data-pipe cycles whatever
+             * the number of lanes, and ~25 of the ~31 ops of a ray are boxes) */
+            if ((h.x & 0xffu) != RTGPU_OP_NODE)
+#endif
+            {
+                double2 b = __ldg(q + 1), c2 = __ldg(q + 2);
+                p[2] = b.x; p[3] = b.y; p[4] = c2.x; p[5] = c2.y;
+            }
         }
     }
     __device__ __forceinline__ void set_best_bounds() {
@@ -527,6 +545,9 @@ __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_
 #define RT_EXTEND_REFILL 16 /* refill when at least this many lanes of the warp are idle (a refill stalls the whole warp on the
                                queue load, three reciprocals and the first op: 16 is 2.7 % faster than 8; 20+ loses lanes) */
 #endif
+#ifndef RT_MEDIUM_QUORUM
+#define RT_MEDIUM_QUORUM 8 /* lanes that must stand on a ConstantMedium before it runs (1 = no hold) */
+#endif
 #ifndef RT_PREFETCH_AHEAD
 #define RT_PREFETCH_AHEAD 16384 /* rays ahead of the fetch counter pulled into L2 at every refill (0 = off; +1 %) */
 #endif
@@ -535,451 +556,117 @@ __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_
                                       warp, so it pays to drain further (24: +1.7 % over 16, 8: -7 %, 32: -3 %) */
 #endif
 #ifndef RT_NODE_UNROLL
-#define RT_NODE_UNROLL 2 /* fetches a lane may consume under one vote; each tests one or two boxes (exec_node) */
+#define RT_NODE_UNROLL 3 /* boxes a lane may test under one vote (A/B on the B200, 192-spp steps: 3 is +1.3 % over 2; 4 is -1 %) */
 #endif
 #ifndef RT_NODE_QUORUM_PCT
 #define RT_NODE_QUORUM_PCT 35 /* keep running NODE rounds while at least this share of the live lanes sits on a NODE */
 #endif
 
-/* ---- the extend loop of one CTA: a pool of rays in shared memory, phases served warp-wide -----------------
- * With one ray per lane (round 1) a warp runs its NODE rounds with ~20 lanes and its leaf tests, one kind after the
- * other, with the 5 - 13 lanes that happen to sit on that kind; the state of an f64 walk also costs 128 registers,
- * i.e. 16 warps per SM.  Here no lane owns a ray.  The CTA keeps RT_POOL_RAYS rays in shared memory (144 B each) and
- * one QUEUE of ray slots per phase:
- *
- *     NODE | SPHERE | BOX | TRI | RECT | MEDIUM | XFORM (PUSH/POP) | EXACT (f64 box test) | FREE
- *
- * A warp repeatedly picks a queue, pops up to 32 slots and runs that ONE phase for 32 different rays -- uniform code,
- * full lanes, registers only for the phase at hand -- then looks at the op each ray meets next and pushes the slot to
- * that op's queue (or, when the walk is over, stores the result and frees the slot).  The NODE phase walks BvhNode
- * boxes with the f32 pre-test until the ray leaves the boxes; the FREE queue feeds the refill phase, which takes the
- * next rays of the global queue.  A ray sits in exactly one queue at a time and meets its ops strictly in program
- * order with its own running best, so results are those of the sequential walk.
- * IO: load(idx, o, d, tm, tmin, tmax, a, b, pos, cur), draw(a, b, pos), store(cur, Closest, pos), prefetch(idx). */
-#ifndef RT_CTA_THREADS
-#define RT_CTA_THREADS 512
-#endif
-#ifndef RT_POOL_RAYS
-#define RT_POOL_RAYS 768 /* rays resident in one CTA's shared memory (<= 1022: a ring entry has 10 bits for slot + 1) */
-#endif
-#define RT_RING_SLOTS 1024
-#ifndef RT_NODE_STEPS
-#define RT_NODE_STEPS 24 /* most NODE fetches one visit of the NODE phase may spend on a ray */
-#endif
-#ifndef RT_NODE_STAY_PCT
-#define RT_NODE_STAY_PCT 50 /* a visit of the NODE phase goes on while this share of its lanes still sits on a box */
-#endif
-enum { PQ_NODE = 0, PQ_SPHERE = 1, PQ_BOX = 2, PQ_TRI = 3, PQ_RECT = 4, PQ_MEDIUM = 5, PQ_XFORM = 6, PQ_EXACT = 7, PQ_FREE = 8, PQ_COUNT = 9 };
-__device__ __forceinline__ uint32_t pool_queue_of_kind(uint32_t kind) {
-    /* NODE SPHERE MSPHERE RECT_XY RECT_XZ RECT_YZ BOX TRI MEDIUM PUSH POP RING, 3 bits each */
-    return (uint32_t)((0466532444110ull >> (3 * kind)) & 7ull);
-}
-struct PushSave { /* one level of the PUSH stack of a pool slot (global scratch: rarely touched, instances only) */
-    double od[6];
-    float c[8];
-};
-struct PoolShared {
-    float4 cA[RT_POOL_RAYS];      /* CullRay: ix iy iz nx */
-    float4 cB[RT_POOL_RAYS];      /*          ny nz e2 tmin */
-    uint4 st[RT_POOL_RAYS];       /* bestL, bestU (f32 bits), i (unit index), sp */
-    double2 od0[RT_POOL_RAYS];    /* o.x o.y */
-    double2 od1[RT_POOL_RAYS];    /* o.z d.x */
-    double2 od2[RT_POOL_RAYS];    /* d.y d.z */
-    double2 tt[RT_POOL_RAYS];     /* shutter time, t_min */
-    double best_t[RT_POOL_RAYS];  /* running best */
-    uint2 best_of[RT_POOL_RAYS];  /* winning unit, box face */
-    uint4 io[RT_POOL_RAYS];       /* random stream (a, b), its position, where the result goes */
-    /* entry of queue position P: (slot + 1) | lap(P) << 10, lap(P) = (P / RT_RING_SLOTS) & 63: a reader of position P
-     * waits for that tag, so a slot of the ring that still holds an older lap (reserved, not written) is never mistaken */
-    uint16_t ring[PQ_COUNT][RT_RING_SLOTS];
-    uint32_t head[16], tail[16];
-    uint32_t in_flight, exhausted;
-};
-static_assert(RT_POOL_RAYS <= 1022 && RT_POOL_RAYS <= RT_RING_SLOTS, "ring entries");
-__device__ __forceinline__ uint32_t ld_vol_u32(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
-__device__ __forceinline__ uint32_t ld_vol_u16(const uint16_t *p) { return *reinterpret_cast<const volatile uint16_t *>(p); }
-
-/* lanes with `valid` append their slot to queue `dest` (one shared-memory atomic per distinct queue) */
-__device__ __forceinline__ void pool_push(PoolShared &S, uint32_t dest, uint32_t slot, bool valid) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t peers = __match_any_sync(0xffffffffu, valid ? dest : 31u);
-    if (valid) {
-        const int leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if ((int)lane == leader) base = atomicAdd(&S.tail[dest], (uint32_t)__popc(peers));
-        base = __shfl_sync(peers, base, leader);
-        const uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-        *reinterpret_cast<volatile uint16_t *>(&S.ring[dest][pos & (RT_RING_SLOTS - 1)]) =
-            (uint16_t)((slot + 1u) | (((pos / RT_RING_SLOTS) & 63u) << 10));
-    }
-}
-/* claims up to 32 entries of queue q for this warp; returns the lane's slot, RT_NO_HIT for lanes without one */
-__device__ __forceinline__ uint32_t pool_pop(PoolShared &S, uint32_t q, uint32_t most = 32u) {
-    const uint32_t lane = threadIdx.x & 31u;
-    uint32_t h0 = 0, cnt = 0;
-    if (lane == 0) {
-        for (;;) {
-            uint32_t hh = ld_vol_u32(&S.head[q]), tt = ld_vol_u32(&S.tail[q]);
-            uint32_t av = tt - hh;
-            if (av == 0u) break;
-            uint32_t c = av < most ? av : most;
-            if (atomicCAS(&S.head[q], hh, hh + c) == hh) {
-                h0 = hh;
-                cnt = c;
-                break;
-            }
-        }
-    }
-    h0 = __shfl_sync(0xffffffffu, h0, 0);
-    cnt = __shfl_sync(0xffffffffu, cnt, 0);
-    uint32_t slot = RT_NO_HIT;
-    if (lane < cnt) {
-        const uint32_t pos = h0 + lane, tag = (pos / RT_RING_SLOTS) & 63u;
-        uint32_t e;
-        do {
-            e = ld_vol_u16(&S.ring[q][pos & (RT_RING_SLOTS - 1)]);
-        } while ((e >> 10) != tag || (e & 1023u) == 0u);
-        slot = (e & 1023u) - 1u;
-    }
-    __threadfence_block(); /* the pusher's writes to the slot's state are visible from here on */
-    return slot;
-}
-
-/* end of every phase: the ray of `slot` stands on unit i.  Past the end: store the result and free the slot;
- * otherwise look at the op there (16-byte header) and queue the slot for its phase. */
+/* The extend loop of one warp (persistent): every lane owns one ray at a time.
+ *  - dynamic fetch: a lane whose ray is finished takes the next ray index from a global counter
+ *    (one atomic per refill of the warp), so trip-count differences do not idle lanes;
+ *  - NODE-first scheduling: while enough lanes sit on a BvhNode box only those run (uniform code, one
+ *    ballot); lanes that reached a leaf wait and then run their leaf op in plain SIMT.
+ * Each ray still executes its own ops strictly in program order with its own running best, so
+ * results are identical to the sequential walk.
+ * IO: load(idx, o, d, tm, tmin, tmax, a, b, pos, cur) -> the ray, the identity (a, b) and position of its random
+ *     stream and where its result goes; draw(a, b, pos) -> next uniform of that stream; store(cur, Closest, pos).
+ * (Two CTA-level designs were built on this walk and measured on the B200 -- leaf requests served warp-wide through
+ *  shared-memory queues, and a full pool of rays in shared memory with one queue per phase: both bit-exact, both
+ *  slower (1 095 and 1 606 against 2 235 Mrays/s): the queue upkeep costs more instructions and L1/shared-memory
+ *  data-pipe cycles than the fuller warps save.  They are in the history of this file, not in the tree.) */
 template <typename IO>
-__device__ __forceinline__ void pool_route(const TravScene ts, PoolShared &S, uint32_t n_units, uint32_t slot, bool valid, uint32_t i,
-                                           bool unsure, IO &io) {
-    uint32_t dest = PQ_FREE;
-    bool finished = false;
-    uint4 w = make_uint4(0, 0, 0, 0);
-    Closest c;
-    c.t = 0.;
-    c.op = RT_NO_HIT;
-    c.face = 0;
-    if (valid) {
-        if (i >= n_units) {
-            finished = true;
-            w = S.io[slot];
-            const uint2 of = S.best_of[slot];
-            c.t = S.best_t[slot];
-            c.op = of.x;
-            c.face = of.y;
-        } else if (unsure) {
-            dest = PQ_EXACT;
-        } else {
-            dest = pool_queue_of_kind(load_op_header(unit_ptr(ts.prog, i)).x & 0xffu);
-        }
-    }
-    const uint32_t freed = __ballot_sync(0xffffffffu, finished);
-    __threadfence_block(); /* state written by this phase before the slot becomes visible in a queue (no global access is pending here) */
-    pool_push(S, dest, slot, valid);
-    if (freed && (threadIdx.x & 31u) == 0) atomicSub(&S.in_flight, (uint32_t)__popc(freed));
-    if (finished) io.store(w.w, c, w.z);
-}
-
-template <typename IO>
-__device__ __forceinline__ void extend_cta_loop(const TravScene ts, uint32_t n_units, uint32_t n, uint32_t *fetch, PushSave *push_scratch,
-                                                IO &io) {
-    extern __shared__ __align__(16) unsigned char rt_smem_raw[];
-    PoolShared &S = *reinterpret_cast<PoolShared *>(rt_smem_raw);
-    const uint32_t T = threadIdx.x, lane = T & 31u;
-    if (T < 16) {
-        S.head[T] = 0;
-        S.tail[T] = T == PQ_FREE ? RT_POOL_RAYS : 0;
-    }
-    if (T == 0) {
-        S.in_flight = 0;
-        S.exhausted = n == 0u ? 1u : 0u;
-    }
-    for (uint32_t k = T; k < PQ_COUNT * RT_RING_SLOTS; k += RT_CTA_THREADS) (&S.ring[0][0])[k] = 0;
-    __syncthreads();
-    for (uint32_t k = T; k < RT_POOL_RAYS; k += RT_CTA_THREADS) S.ring[PQ_FREE][k] = (uint16_t)(k + 1u); /* lap 0 */
-    __syncthreads();
-    PushSave *const my_push = push_scratch + (size_t)blockIdx.x * RT_POOL_RAYS * RT_MAX_PUSH;
-
+__device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_units, uint32_t n, uint32_t *fetch, IO &io) {
+    const uint32_t lane = threadIdx.x & 31u;
+    Traversal<RayRegs> tr;
+    SavedRays stk;
+    bool active = false, exhausted = false;
+    uint32_t rng_a = 0, rng_b = 0, rng_pos = 0, cur = 0;
+    const int refill_at = io.refill_at();
     for (;;) {
-        /* what is there to do?  lane q looks at queue q */
-        uint32_t avail = 0;
-        if (lane < PQ_COUNT) avail = ld_vol_u32(&S.tail[lane]) - ld_vol_u32(&S.head[lane]);
-        const uint32_t exhausted = ld_vol_u32(&S.exhausted);
-        const uint32_t free_n = __shfl_sync(0xffffffffu, avail, PQ_FREE);
-        const uint32_t work = lane < PQ_FREE ? avail : 0u;
-        /* the fullest work queue (a full batch of 32 is as good as it gets) */
-        const uint32_t score = __reduce_max_sync(0xffffffffu, (umin(work, 32u) << 8) | (work ? (lane + 1u) : 0u));
-        uint32_t q = PQ_COUNT;
-        if ((score >> 8) >= 32u) q = (score & 0xffu) - 1u;
-        else if (!exhausted && free_n >= 32u) q = PQ_FREE;
-        else if (score >> 8) q = (score & 0xffu) - 1u;
-        else if (!exhausted && free_n) q = PQ_FREE;
-        if (q == PQ_COUNT) {
-            if (exhausted && ld_vol_u32(&S.in_flight) == 0u) break;
-            __nanosleep(32);
-            continue;
-        }
-
-        if (q == PQ_FREE) { /* ---- refill: the next rays of the global queue move into free slots ---- */
-            uint32_t slot = pool_pop(S, PQ_FREE);
-            const uint32_t got = __ballot_sync(0xffffffffu, slot != RT_NO_HIT);
-            if (!got) continue;
+        uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= refill_at)) {
+            int leader = __ffs(idle) - 1;
             uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(fetch, (uint32_t)__popc(got));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const uint32_t idx = base + (uint32_t)__popc(got & ((1u << lane) - 1u));
-            bool valid = slot != RT_NO_HIT && idx < n;
-            const uint32_t loaded = __ballot_sync(0xffffffffu, valid);
-            if (lane == 0) { /* in_flight first: a warp that sees `exhausted` must also see the rays this refill brings in */
-                if (loaded) atomicAdd(&S.in_flight, (uint32_t)__popc(loaded));
-                __threadfence_block();
-                if (base + (uint32_t)__popc(got) >= n) *reinterpret_cast<volatile uint32_t *>(&S.exhausted) = 1u;
-            }
-            if (valid) {
+            if ((int)lane == leader) base = atomicAdd(fetch, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            exhausted = base + (uint32_t)__popc(idle) >= n;
+            if (!active) {
+                uint32_t idx = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
 #if RT_PREFETCH_AHEAD > 0
                 if (idx + RT_PREFETCH_AHEAD < n) io.prefetch(idx + RT_PREFETCH_AHEAD);
 #endif
-                V3 o, d;
-                double tm, tmin, tmax;
-                uint32_t a, b, pos, cur;
-                io.load(idx, o, d, tm, tmin, tmax, a, b, pos, cur);
-                CullRay c;
-                cull_ray_setup(c, o.x, o.y, o.z, 1. / d.x, 1. / d.y, 1. / d.z, tmin, ts.extent); /* 1/d: aabb.rs:17 */
-                S.cA[slot] = make_float4(c.ix, c.iy, c.iz, c.nx);
-                S.cB[slot] = make_float4(c.ny, c.nz, c.e2, c.tmin);
-                S.st[slot] = make_uint4(__float_as_uint(rt_f32_down(tmax)), __float_as_uint(rt_f32_up(tmax)), 0u, 0u);
-                S.od0[slot] = make_double2(o.x, o.y);
-                S.od1[slot] = make_double2(o.z, d.x);
-                S.od2[slot] = make_double2(d.y, d.z);
-                S.tt[slot] = make_double2(tm, tmin);
-                S.best_t[slot] = tmax;
-                S.best_of[slot] = make_uint2(RT_NO_HIT, 0u);
-                S.io[slot] = make_uint4(a, b, pos, cur);
+                if (idx < n) {
+                    V3 o, d;
+                    double tm, tmin, tmax;
+                    io.load(idx, o, d, tm, tmin, tmax, rng_a, rng_b, rng_pos, cur);
+                    tr.start(ts, 0, n_units, o, d, tm, tmin, tmax);
+                    active = !tr.done();
+                    if (!active) io.store(cur, tr.best, rng_pos);
+                }
             }
-            /* slots whose ray index fell past the end go straight back to FREE */
-            const bool spare = slot != RT_NO_HIT && !valid;
-            pool_push(S, PQ_FREE, slot, spare);
-            pool_route(ts, S, n_units, slot, valid, 0u, false, io);
-            continue;
+            idle = __ballot_sync(0xffffffffu, !active);
         }
-
-        const uint32_t slot = pool_pop(S, q);
-        const bool valid = slot != RT_NO_HIT;
-        if (!__any_sync(0xffffffffu, valid)) continue;
-
-        if (q == PQ_NODE) { /* ---- BvhNode boxes, f32 pre-test, until the ray leaves the boxes ---- */
-            CullRay c;
-            float bestL = 0.f, bestU = 0.f;
-            uint32_t i = n_units;
-            bool in_node = false, unsure = false;
-            uint4 h = make_uint4(0, 0, 0, 0);
-            double p[6] = {0., 0., 0., 0., 0., 0.};
-            if (valid) {
-                const float4 a = S.cA[slot], b = S.cB[slot];
-                const uint4 st = S.st[slot];
-                c.ix = a.x; c.iy = a.y; c.iz = a.z; c.nx = a.w;
-                c.ny = b.x; c.nz = b.y; c.e2 = b.z; c.tmin = b.w;
-                bestL = __uint_as_float(st.x);
-                bestU = __uint_as_float(st.y);
-                i = st.z;
-                const uint4 *op = unit_ptr(ts.prog, i);
-                h = load_op_header(op);
-                load_op_payload(op, p);
-                in_node = true; /* whoever queued the slot here saw a NODE at unit i */
-            }
-            const uint32_t stay = max(1u, ((uint32_t)__popc(__ballot_sync(0xffffffffu, valid)) * RT_NODE_STAY_PCT) / 100u);
+        if (idle == 0xffffffffu) break; /* no lane has a ray and none is left to fetch */
+        /* NODE rounds: as long as enough lanes sit on a BvhNode box, run only those (uniform code,
+         * one ballot of overhead); lanes that reached a leaf wait.  Then every waiting lane runs its
+         * leaf op once (plain SIMT over the few leaf kinds) and the cycle repeats. */
+        const uint32_t n_active = 32u - (uint32_t)__popc(idle);
+        const uint32_t node_quorum = max(1u, (n_active * RT_NODE_QUORUM_PCT) / 100u);
+        bool node_ran = false;
 #pragma unroll 1
-            for (int step = 0; step < RT_NODE_STEPS; ++step) {
-                if ((uint32_t)__popc(__ballot_sync(0xffffffffu, in_node)) < stay) break;
-                if (in_node) {
-                    /* BvhNode::hit's box test (bvh/mod.rs:87) for the NODE at unit i and -- same fetch -- for the NODE that
-                     * follows it, if any: its left child, tested next anyway when the first box is hit */
-                    const int ra = cull_box(c, __uint_as_float(h.z), __uint_as_float(h.w), lo_f32(p[0]), hi_f32(p[0]), lo_f32(p[1]),
-                                            hi_f32(p[1]), bestL, bestU);
-                    const uint32_t bw = (uint32_t)__double2loint(p[2]), bskip = (uint32_t)__double2hiint(p[2]);
-                    const int rb = cull_box(c, lo_f32(p[3]), hi_f32(p[3]), lo_f32(p[4]), hi_f32(p[4]), lo_f32(p[5]), hi_f32(p[5]), bestL,
-                                            bestU);
-                    if (ra == RT_CULL_UNSURE) {
-                        unsure = true;
-                        in_node = false;
-                    } else {
-                        uint32_t nxt = i + 1; /* first box hit; what follows is a leaf, or a NODE the pre-test could not decide */
-                        if (ra == RT_CULL_MISS) nxt = h.y;
-#if RT_NODE_PAIR
-                        else if ((bw & 0xffu) == RTGPU_OP_NODE && rb != RT_CULL_UNSURE) nxt = rb == RT_CULL_MISS ? bskip : i + 2;
+        for (;;) {
+            bool in_node = active && tr.phase() == PH_NODE;
+            uint32_t m = __ballot_sync(0xffffffffu, in_node);
+            if ((uint32_t)__popc(m) < node_quorum) break;
+            node_ran = true;
+            if (in_node) {
+                tr.exec_node(ts);
+#if RT_NODE_UNROLL >= 2
+                if (!tr.done() && tr.phase() == PH_NODE) tr.exec_node(ts); /* second box under the same vote */
 #endif
-                        i = nxt;
-                        if (i < n_units) {
-                            const uint4 *op = unit_ptr(ts.prog, i);
-                            h = load_op_header(op);
-                            load_op_payload(op, p);
-                            in_node = (h.x & 0xffu) == RTGPU_OP_NODE;
-                        } else {
-                            in_node = false;
-                        }
-                    }
+#if RT_NODE_UNROLL >= 3
+                if (!tr.done() && tr.phase() == PH_NODE) tr.exec_node(ts);
+#endif
+#if RT_NODE_UNROLL >= 4
+                if (!tr.done() && tr.phase() == PH_NODE) tr.exec_node(ts);
+#endif
+                if (tr.done()) {
+                    io.store(cur, tr.best, rng_pos);
+                    active = false;
                 }
             }
-            if (valid) S.st[slot].z = i;
-            /* the op at i is in registers already: route without another fetch */
-            uint32_t dest = PQ_FREE;
-            bool finished = false;
-            uint4 w = make_uint4(0, 0, 0, 0);
-            Closest cl;
-            cl.t = 0.;
-            cl.op = RT_NO_HIT;
-            cl.face = 0;
-            if (valid) {
-                if (i >= n_units) {
-                    finished = true;
-                    w = S.io[slot];
-                    const uint2 of = S.best_of[slot];
-                    cl.t = S.best_t[slot];
-                    cl.op = of.x;
-                    cl.face = of.y;
-                } else {
-                    dest = unsure ? (uint32_t)PQ_EXACT : pool_queue_of_kind(h.x & 0xffu);
-                }
-            }
-            const uint32_t freed = __ballot_sync(0xffffffffu, finished);
-            __threadfence_block();
-            pool_push(S, dest, slot, valid);
-            if (freed && lane == 0) atomicSub(&S.in_flight, (uint32_t)__popc(freed));
-            if (finished) io.store(w.w, cl, w.z);
-            continue;
         }
-
-        /* ---- every other phase works on ONE op of each ray ---- */
-        uint32_t i = n_units;
-        bool unsure = false;
-        if (valid) {
-            i = S.st[slot].z;
-            const uint4 *op = unit_ptr(ts.prog, i);
-            const uint4 h = load_op_header(op);
-            const uint32_t kind = h.x & 0xffu;
-            const double2 a0 = S.od0[slot], a1 = S.od1[slot], a2 = S.od2[slot];
-            V3 o = v3(a0.x, a0.y, a1.x), d = v3(a1.y, a2.x, a2.y);
-            if (q == PQ_XFORM) { /* PUSH / POP: Translate, RotateY, Zoom around a subtree (hittable/mod.rs:165-174,235-264,321-330) */
-                uint32_t sp = S.st[slot].w;
-                PushSave *sv = my_push + (size_t)slot * RT_MAX_PUSH;
-                if (kind == RTGPU_OP_PUSH) {
-                    const float4 ca = S.cA[slot], cb = S.cB[slot];
-                    PushSave &e = sv[sp];
-                    e.od[0] = o.x; e.od[1] = o.y; e.od[2] = o.z; e.od[3] = d.x; e.od[4] = d.y; e.od[5] = d.z;
-                    e.c[0] = ca.x; e.c[1] = ca.y; e.c[2] = ca.z; e.c[3] = ca.w; e.c[4] = cb.x; e.c[5] = cb.y; e.c[6] = cb.z; e.c[7] = cb.w;
-                    ++sp;
-                    for (uint32_t j = 0; j < h.w; ++j) {
-                        rtgpu_xform xf = load_xform(ts, h.z + j);
-                        xform_ray(xf, o, d);
-                    }
-                    CullRay c;
-                    cull_ray_setup(c, o.x, o.y, o.z, 1. / d.x, 1. / d.y, 1. / d.z, S.tt[slot].y, ts.extent);
-                    S.cA[slot] = make_float4(c.ix, c.iy, c.iz, c.nx);
-                    S.cB[slot] = make_float4(c.ny, c.nz, c.e2, c.tmin);
-                } else {
-                    --sp;
-                    const PushSave &e = sv[sp];
-                    o = v3(e.od[0], e.od[1], e.od[2]);
-                    d = v3(e.od[3], e.od[4], e.od[5]);
-                    S.cA[slot] = make_float4(e.c[0], e.c[1], e.c[2], e.c[3]);
-                    S.cB[slot] = make_float4(e.c[4], e.c[5], e.c[6], e.c[7]);
-                }
-                S.od0[slot] = make_double2(o.x, o.y);
-                S.od1[slot] = make_double2(o.z, d.x);
-                S.od2[slot] = make_double2(d.y, d.z);
-                S.st[slot].w = sp;
-                i += 2;
-            } else {
-                const double2 tt = S.tt[slot];
-                const double tmin = tt.y;
-                double best = S.best_t[slot];
-                if (q == PQ_EXACT) { /* AABB::hit (aabb.rs:15-32) in f64 on the f64 box of the NODE at unit i */
-                    const double2 *bq = ts.boxes64 + 3 * (size_t)(h.x >> 8);
-                    double2 b0 = __ldg(bq), b1 = __ldg(bq + 1), b2 = __ldg(bq + 2);
-                    double bx[6] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y};
-                    V3 inv = v3(1. / d.x, 1. / d.y, 1. / d.z);
-                    RaySigns sg;
-                    sg.m = (inv.x < 0. ? 1u : 0u) | (inv.y < 0. ? 2u : 0u) | (inv.z < 0. ? 4u : 0u);
-                    i = hit_aabb(o, inv, sg, bx, tmin, best) ? i + 1 : h.y;
-                } else {
-                    double p[6];
-                    load_op_payload(op, p);
-                    uint32_t face = 0;
-                    bool hit = false;
-                    uint32_t next = i + 2;
-                    if (q == PQ_SPHERE) {
-                        V3 c0 = v3(p[0], p[1], p[2]);
-                        if (kind == RTGPU_OP_MSPHERE) { /* MovingSphere::center, sphere.rs:124-127 */
-                            double qq[8];
-                            load_slot8(op + 4, qq);
-                            c0 = c0 + (v3(qq[0], qq[1], qq[2]) - c0) * ((tt.x - p[4]) / (p[5] - p[4]));
-                            next = i + 4;
-                        }
-                        hit = hit_sphere(o, d, length_sqr(d), c0, p[3], tmin, best);
-                    } else if (q == PQ_BOX) {
-                        hit = hit_box(o, d, p, tmin, best, face);
-                    } else if (q == PQ_TRI) {
-                        double qq[8];
-                        load_slot8(op + 4, qq);
-                        hit = hit_triangle(o, d, v3(p[0], p[1], p[2]), v3(p[3], p[4], p[5]), v3(qq[0], qq[1], qq[2]), v3(qq[3], qq[4], qq[5]),
-                                           tmin, best);
-                        next = i + 4;
-                    } else if (q == PQ_RECT) {
-                        if (kind == RTGPU_OP_RECT_XY) hit = hit_rect<2>(o, d, p[0], p[1], p[2], p[3], p[4], tmin, best);
-                        else if (kind == RTGPU_OP_RECT_XZ) hit = hit_rect<1>(o, d, p[0], p[1], p[2], p[3], p[4], tmin, best);
-                        else if (kind == RTGPU_OP_RECT_YZ) hit = hit_rect<0>(o, d, p[0], p[1], p[2], p[3], p[4], tmin, best);
-                        else hit = hit_ring(o, d, p[0], p[1], tmin, best);
-                    } else { /* ConstantMedium::hit, constantmedium.rs:49-83 */
-                        double t1 = CUDART_INF, t2 = CUDART_INF;
-                        bool h1, h2 = false;
-                        const double a = length_sqr(d);
-                        bool single_sphere = h.y == i + 4;
-                        if (single_sphere) single_sphere = (load_op_header(op + 4).x & 0xffu) == RTGPU_OP_SPHERE;
-                        if (single_sphere) { /* boundary = one Sphere (both media of final_scene) */
-                            double bp[6];
-                            load_op_payload(op + 4, bp);
-                            V3 c0 = v3(bp[0], bp[1], bp[2]);
-                            h1 = hit_sphere(o, d, a, c0, bp[3], -CUDART_INF, t1);
-                            if (h1) h2 = hit_sphere(o, d, a, c0, bp[3], t1 + 0.0001, t2);
-                        } else {
-                            Closest r1 = closest_hit_boundary(ts, i + 2, h.y, o, d, tt.x, -CUDART_INF, CUDART_INF);
-                            h1 = r1.op != RT_NO_HIT;
-                            t1 = r1.t;
-                            if (h1) {
-                                Closest r2 = closest_hit_boundary(ts, i + 2, h.y, o, d, tt.x, t1 + 0.0001, CUDART_INF);
-                                h2 = r2.op != RT_NO_HIT;
-                                t2 = r2.t;
-                            }
-                        }
-                        if (h1 && h2) {
-                            t1 = fmax(t1, tmin);
-                            t2 = fmin(t2, best);
-                            if (!(t1 >= t2)) {
-                                t1 = fmax(t1, 0.);
-                                double ray_length = sqrt(a);
-                                double distance_inside_boundary = (t2 - t1) * ray_length;
-                                uint4 w = S.io[slot];
-                                double rnd = io.draw(w.x, w.y, w.z); /* the ray's stream, in visiting order */
-                                S.io[slot].z = w.z;
-                                double hit_distance = p[0] * log(rnd); /* neg_inv_density * rnd.log(E) */
-                                if (!(hit_distance > distance_inside_boundary)) {
-                                    best = t1 + hit_distance / ray_length;
-                                    hit = true;
-                                }
-                            }
-                        }
-                        next = h.y;
-                    }
-                    if (hit) {
-                        S.best_t[slot] = best;
-                        S.best_of[slot] = make_uint2(i, face);
-                        S.st[slot].x = __float_as_uint(rt_f32_down(best));
-                        S.st[slot].y = __float_as_uint(rt_f32_up(best));
-                    }
-                    i = next;
-                }
+        /* expensive leaves are held back until enough lanes want the same code: a ConstantMedium costs ~300
+         * instructions (two boundary hits, Philox, log) and every ray of a foggy scene meets it, so the
+         * lanes standing on one pile up quickly; they run together instead of 5 at a time. */
+        bool hold = false;
+#if RT_MEDIUM_QUORUM > 1
+        {
+            bool at_medium = active && !tr.unsure && (tr.h.x & 0xffu) == RTGPU_OP_MEDIUM;
+            uint32_t mm = __ballot_sync(0xffffffffu, at_medium);
+            if (mm) {
+                /* hold only while something else certainly advances this iteration (a NODE round ran, or another
+                 * lane runs a different leaf below); lanes on a NODE under the node quorum do NOT count */
+                uint32_t other_leaf = __ballot_sync(0xffffffffu, active && !at_medium && tr.phase() != PH_NODE);
+                hold = at_medium && (uint32_t)__popc(mm) < (uint32_t)RT_MEDIUM_QUORUM && (node_ran || other_leaf != 0u);
             }
-            S.st[slot].z = i;
         }
-        pool_route(ts, S, n_units, slot, valid, i, unsure, io);
+#endif
+        if (active && !hold) {
+            switch (tr.phase()) {
+            case PH_NODE: break; /* below the quorum: waits for the next NODE rounds */
+            case PH_EXACT: tr.exec_node_exact(ts); break;
+            case PH_SPHERE: tr.exec_sphere(ts); break;
+            case PH_BOX: tr.exec_box(ts); break;
+            case PH_TRI: tr.exec_tri(ts); break;
+            default: tr.template exec_misc<true>(ts, stk, [&]() { return io.draw(rng_a, rng_b, rng_pos); }); break;
+            }
+            if (tr.done()) {
+                io.store(cur, tr.best, rng_pos);
+                active = false;
+            }
+        }
     }
 }
 

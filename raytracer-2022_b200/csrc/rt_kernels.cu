@@ -1,24 +1,29 @@
 /*
  * rt_kernels.cu -- wavefront path tracer for sm_100a and the C ABI of include/rtgpu.h.
  *
- * One wave = S samples of every pixel, all in flight at once (paths = S * W * H).  Per bounce:
+ * A render keeps a bounded POOL of paths in flight (path regeneration): one queue entry per live path, two queues
+ * that swap roles.  Per iteration, all on one stream and without a host round trip:
  *
- *   (sort)     bounces with enough rays are walked in the order of a 32-bit origin-cell / direction key that the
- *              shade kernels wrote next to every ray; only (key, entry) pairs are sorted, the records stay put
- *   k_extend   closest hit of every live ray against the flat traversal program
- *              (BvhNode::hit, hittable/bvh/mod.rs:86-101, unrolled -- rt_device.cuh)
- *   k_classify bins the hits by material class into index lists
- *   k_shade<C> one kernel per class: HitRecord of the winner, emitted/scatter/MixturePdf (ray_color,
- *              main.rs:233-278), survivors appended to the next queue with one warp-aggregated atomic
- *              (ballot + popc prefix) -- the compaction between bounces
+ *   k_iter_begin  resets the per-iteration counters on the device
+ *   k_regen       tops the queue up with new camera rays while samples remain (main.rs:145-149, camera.rs:64-73),
+ *                 so every launch below carries a full queue whatever the depth of its paths
+ *   (sort)        the queue is walked in the order of a 32-bit origin-cell / direction key that k_regen and the
+ *                 shade kernels wrote next to every ray; only (key, entry) pairs are sorted, the records stay put
+ *   k_extend      closest hit of every ray against the flat traversal program
+ *                 (BvhNode::hit, hittable/bvh/mod.rs:86-101, unrolled -- rt_device.cuh)
+ *   k_classify    bins the hits by material class into index lists
+ *   k_shade<C>    one kernel per class: HitRecord of the winner, emitted/scatter/MixturePdf (ray_color,
+ *                 main.rs:233-278); survivors are appended to the other queue with one warp-aggregated atomic
+ *                 (ballot + popc prefix) -- the compaction between bounces; a path that ends adds its radiance to
+ *                 its pixel
  *
- * A queue entry is a 64-byte ray record plus a 32-byte state record; the queue length stays on the device
- * (k_extend/k_shade of bounce b read counts[b], k_shade bumps counts[b+1]), so a wave is enqueued with one
- * 4-byte readback per sorted bounce (the sort needs the length) or per 8 bounces.  Every path writes its
- * radiance exactly once, to contrib[path id], when it ends (miss / light / absorbed); k_accumulate then sums the
- * S samples of a pixel in a fixed order, which makes the image independent of scheduling and of the ray order.
+ * Queue lengths, the sample cursor and the ray counters live in a control block on the device (WaveCtl); the host
+ * reads a 32-byte snapshot of it asynchronously every iteration and only uses it to stop issuing iterations.
+ * Pixel sums are exact: every contribution is added as a 64-bit fixed-point integer (2^-32 units), so the sum does
+ * not depend on the order in which paths end and the image is bit-reproducible (k_finish converts to float).
  * Randomness: one Philox slot stream per path, keyed (seed, pixel, sample) -- include/rt_rng.h.
  */
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -56,6 +61,7 @@ constexpr int kThreads = RT_THREADS;
 #define RT_SHADE_BLOCKS_PER_SM 8 /* 16 warps/SM: measured best (5 % over 32 warps/SM) */
 #endif
 constexpr int kShadeThreads = RT_SHADE_THREADS;
+
 constexpr int kSMs = 148;
 #ifndef RT_BLOCKS_PER_SM
 #define RT_BLOCKS_PER_SM 8
@@ -67,9 +73,11 @@ constexpr int kBlocksPerSM = RT_BLOCKS_PER_SM;
  * through the per-class index lists, touch 3 sectors per path instead of the 12 an SoA layout costs. */
 struct __align__(16) RayRec {
     double ox, oy, oz, dx, dy, dz, tm;
-    uint32_t pid; /* path id inside the wave */
-    uint32_t rng; /* next slot of the path's Philox stream */
+    uint32_t pid; /* path id inside the render call: sample-major, pixel = pid % npix */
+    uint32_t rng; /* next slot of the path's Philox stream (low 20 bits) | segments the path may still trace << 20 */
 };
+#define RT_POS_BITS 20
+#define RT_POS_MASK ((1u << RT_POS_BITS) - 1u)
 struct __align__(16) StateRec {
     double bx, by, bz, pad_; /* throughput */
 };
@@ -126,16 +134,39 @@ __device__ __forceinline__ void st_beta(StateRec *p, V3 b) {
     q[0] = make_double2(b.x, b.y);
     q[1] = make_double2(b.z, 0.);
 }
-struct HitBuf {
-    double *t;
-    uint32_t *op;  /* op index | box face << 29; RT_NO_HIT = miss */
-    uint32_t *rng; /* the path's Philox slot after the walk (media draw): a 4-byte array of its own -- written back into the
-                      64-byte ray record it dirtied one 32-byte sector per ray, 28 B/ray of DRAM writes for nothing */
+/* what k_extend leaves for the shade kernels: ONE 16-byte record per queue entry (one sector write per ray) */
+struct __align__(16) HitRec16 {
+    double t;
+    uint32_t op;  /* unit index | box face << 29; RT_NO_HIT = miss */
+    uint32_t rng; /* the path's Philox slot after the walk (ConstantMedium draws) */
 };
+struct HitBuf {
+    HitRec16 *rec;
+};
+__device__ __forceinline__ HitRec16 ld_hit(const HitRec16 *p) {
+    uint4 v = *reinterpret_cast<const uint4 *>(p);
+    HitRec16 h;
+    h.t = __hiloint2double((int)v.y, (int)v.x);
+    h.op = v.z;
+    h.rng = v.w;
+    return h;
+}
 struct WaveParams {
     uint64_t seed;
     uint32_t first_pixel, npix_wave, sample_begin, n_paths;
     int32_t width, height;
+    uint32_t max_depth, pool; /* segments per path (main.rs:39); paths kept in flight */
+};
+/* control block of a render on the device */
+struct WaveCtl {
+    uint32_t count[2];       /* entries of queue 0 / 1 */
+    uint32_t gen_next;       /* next path id to generate */
+    uint32_t fetch;          /* k_extend's ray cursor */
+    uint32_t class_count[8]; /* entries of the class lists of this iteration */
+    unsigned long long rays; /* closest-hit queries so far */
+    uint32_t iter;
+    uint32_t n_old; /* entries of the current queue that come from the last bounce (the rest are new camera rays) */
+    unsigned long long len_hist[RTGPU_MAX_BOUNCE_STATS + 1]; /* paths by number of segments traced */
 };
 
 __device__ __forceinline__ void path_rng(rt_rng &rng, const WaveParams &wp, uint32_t pid, uint32_t pos) {
@@ -164,18 +195,32 @@ __device__ __forceinline__ Ray camera_ray(const rtgpu_camera &cam, int x, int y,
     return r;
 }
 
-__global__ void __launch_bounds__(kThreads) k_raygen(DScene sc, PathQueue q, WaveParams wp) {
-    uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x; pid < wp.n_paths; pid += stride) {
-        uint32_t pixel = wp.first_pixel + pid % wp.npix_wave;
-        rt_rng rng;
-        path_rng(rng, wp, pid, 0);
-        Ray r = camera_ray(sc.cam, (int)(pixel % (uint32_t)wp.width), (int)(pixel / (uint32_t)wp.width), wp.width, wp.height, rng);
-        st_ray(q.ray + pid, r.o, r.d, r.tm, pid, rng.pos);
-        st_beta(q.st + pid, v3(1., 1., 1.));
+/* start of an iteration: the rays of queue `cur` are about to be extended */
+__global__ void k_iter_begin(WaveCtl *ctl, int cur) {
+    if (threadIdx.x == 0) {
+        ctl->fetch = 0;
+        ctl->count[cur ^ 1] = 0;
+        ctl->iter += 1;
     }
+    if (threadIdx.x < 8) ctl->class_count[threadIdx.x] = 0;
 }
-
+/* after k_regen: the queue is complete; its length is this iteration's ray count */
+__global__ void k_regen_commit(WaveCtl *ctl, int cur, WaveParams wp) {
+    uint32_t cnt = ctl->count[cur];
+    uint32_t room = wp.pool > cnt ? wp.pool - cnt : 0u, left = wp.n_paths - ctl->gen_next;
+    uint32_t add = room < left ? room : left;
+    ctl->n_old = cnt;
+    ctl->count[cur] = cnt + add;
+    ctl->gen_next += add;
+    ctl->rays += (unsigned long long)(cnt + add);
+}
+/* Only the survivors of the last bounce are sorted: the new camera rays behind them are neighbouring pixels already.  The
+ * sort runs over a host-side upper bound of the number of survivors; entries past them get the largest key, and since the
+ * pair sort is stable and the values ascend they stay where they are (perm[k] = k there). */
+__global__ void k_pad_keys(const WaveCtl *ctl, uint32_t *keys, uint32_t pad_to) {
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = ctl->n_old + blockIdx.x * blockDim.x + threadIdx.x; i < pad_to; i += stride) keys[i] = 0xffffffffu;
+}
 /* world.hit(r, 0.001, f64::MAX), main.rs:243 -- persistent warps, see extend_warp_loop */
 #ifndef RT_EXTEND_MIN_BLOCKS
 #define RT_EXTEND_MIN_BLOCKS 4
@@ -185,9 +230,10 @@ struct QueueIO {
     HitBuf hb;
     WaveParams wp;
     const uint32_t *perm; /* sorted order -> queue entry (ray reordering without moving the records), or nullptr */
+    uint32_t n_perm;      /* entries covered by perm (the survivors of the last bounce); the new camera rays behind them are walked in place */
     __device__ __forceinline__ void load(uint32_t idx, V3 &o, V3 &d, double &tm, double &tmin, double &tmax, uint32_t &a, uint32_t &b,
                                          uint32_t &pos, uint32_t &cur) {
-        if (perm) idx = __ldg(perm + idx);
+        if (idx < n_perm) idx = __ldg(perm + idx);
         RayRec rr = ld_ray_stream(q.ray + idx);
         o = v3(rr.ox, rr.oy, rr.oz);
         d = v3(rr.dx, rr.dy, rr.dz);
@@ -196,9 +242,10 @@ struct QueueIO {
         tmax = RT_F64_MAX;
         a = rr.pid; /* the path's Philox stream: (pixel, sample) follow from the path id */
         b = 0;
-        pos = rr.rng;
+        pos = rr.rng & RT_POS_MASK;
         cur = idx;
     }
+    __device__ __forceinline__ int refill_at() const { return perm ? RT_EXTEND_REFILL_SORTED : RT_EXTEND_REFILL; }
     /* pulls a queue entry that some warp will ask for a few microseconds from now into L2 */
     __device__ __forceinline__ void prefetch(uint32_t idx) {
         if (!perm) asm volatile("prefetch.global.L2 [%0];" ::"l"(q.ray + idx));
@@ -211,25 +258,27 @@ struct QueueIO {
         return u;
     }
     __device__ __forceinline__ void store(uint32_t idx, const Closest &c, uint32_t pos) {
+        uint4 v;
+        v.x = (uint32_t)__double2loint(c.t);
+        v.y = (uint32_t)__double2hiint(c.t);
+        v.z = c.op == RT_NO_HIT ? RT_NO_HIT : (c.op | (c.face << 29));
+        v.w = pos;
 #if RT_STREAM_HINTS
-        __stcs(hb.t + idx, c.t);
-        __stcs(hb.op + idx, c.op == RT_NO_HIT ? RT_NO_HIT : (c.op | (c.face << 29)));
-        __stcs(hb.rng + idx, pos);
+        __stcs(reinterpret_cast<uint4 *>(hb.rec + idx), v);
 #else
-        hb.t[idx] = c.t;
-        hb.op[idx] = c.op == RT_NO_HIT ? RT_NO_HIT : (c.op | (c.face << 29));
-        hb.rng[idx] = pos;
+        *reinterpret_cast<uint4 *>(hb.rec + idx) = v;
 #endif
     }
 };
-__global__ void __launch_bounds__(RT_CTA_THREADS, 1) k_extend(DScene sc, PathQueue q, HitBuf hb, const uint32_t *count, uint32_t *fetch,
-                                                             WaveParams wp, const uint32_t *perm, PushSave *push_scratch) {
+__global__ void __launch_bounds__(kThreads, RT_EXTEND_MIN_BLOCKS) k_extend(DScene sc, PathQueue q, HitBuf hb, WaveCtl *ctl, int cur,
+                                                                           WaveParams wp, const uint32_t *perm, uint32_t n_perm) {
     QueueIO io;
     io.q = q;
     io.hb = hb;
     io.wp = wp;
     io.perm = perm;
-    extend_cta_loop(trav_of(sc), sc.n_units, *count, fetch, push_scratch, io);
+    io.n_perm = perm ? n_perm : 0u;
+    extend_warp_loop(trav_of(sc), sc.n_units, ctl->count[cur], &ctl->fetch, io);
 }
 
 /* ---- ray reordering between bounces ---------------------------------------------------------------
@@ -279,15 +328,16 @@ __device__ __forceinline__ uint32_t ray_sort_key(const SortGrid &g, V3 ro, V3 rd
     else if (RT_SORT_DIR_BITS == 6) dq = ((uint32_t)fminf(ax * sc, 7.f) << 3) | (uint32_t)fminf(ay * sc, 7.f);
     return (((morton << 3) | oct) << RT_SORT_DIR_BITS) | dq;
 }
-/* moments of the first hit points of a wave (every 8th camera ray) */
-__global__ void k_sort_moments(PathQueue q, HitBuf hb, const uint32_t *count, double *moments /* sum xyz, sum xyz^2, n */) {
-    uint32_t n = *count;
+/* moments of the first hit points of a render (every 8th ray of the first iteration: camera rays) */
+__global__ void k_sort_moments(PathQueue q, HitBuf hb, const WaveCtl *ctl, int cur, double *moments /* sum xyz, sum xyz^2, n */) {
+    uint32_t n = ctl->count[cur];
     double s1[3] = {0., 0., 0.}, s2[3] = {0., 0., 0.}, cnt = 0.;
     uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * 8u; i < n; i += stride * 8u) {
-        if (hb.op[i] == RT_NO_HIT) continue;
+        HitRec16 hr = ld_hit(hb.rec + i);
+        if (hr.op == RT_NO_HIT) continue;
         RayRec rr = ld_ray(q.ray + i);
-        double t = hb.t[i];
+        double t = hr.t;
         double x = rr.ox + t * rr.dx, y = rr.oy + t * rr.dy, z = rr.oz + t * rr.dz;
         if (fabs(x) < 1e30 && fabs(y) < 1e30 && fabs(z) < 1e30) {
             s1[0] += x; s1[1] += y; s1[2] += z;
@@ -325,6 +375,25 @@ __global__ void k_iota(uint32_t *p, uint32_t n) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = i;
 }
 
+/* Path regeneration: while samples remain, the queue of the coming iteration is topped up to `pool` entries with new
+ * camera rays (main.rs:145-149 + Camera::get_ray).  Paths are generated in path-id order = sample-major, so the new
+ * rays of one launch are neighbouring pixels of the same sample.  k_regen_commit then publishes the new length. */
+__global__ void __launch_bounds__(kThreads) k_regen(DScene sc, PathQueue q, const WaveCtl *ctl, int cur, WaveParams wp) {
+    const uint32_t cnt = ctl->count[cur], first = ctl->gen_next;
+    const uint32_t room = wp.pool > cnt ? wp.pool - cnt : 0u, left = wp.n_paths - first;
+    const uint32_t add = room < left ? room : left;
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < add; k += stride) {
+        uint32_t pid = first + k;
+        uint32_t pixel = wp.first_pixel + pid % wp.npix_wave;
+        rt_rng rng;
+        path_rng(rng, wp, pid, 0);
+        Ray r = camera_ray(sc.cam, (int)(pixel % (uint32_t)wp.width), (int)(pixel / (uint32_t)wp.width), wp.width, wp.height, rng);
+        st_ray(q.ray + cnt + k, r.o, r.d, r.tm, pid, rng.pos | (wp.max_depth << RT_POS_BITS));
+        st_beta(q.st + cnt + k, v3(1., 1., 1.));
+    }
+}
+
 /* ---- shading, split by material class ------------------------------------------------------------
  * One monolithic shade kernel was 130 KB of SASS executed by warps whose lanes sat on five different
  * materials: ncu showed 6.7 active lanes per instruction and `no_instruction` (instruction-cache miss)
@@ -336,16 +405,17 @@ __global__ void k_iota(uint32_t *p, uint32_t n) {
  *   class 3  Metal            class 4  Dielectric                class 5  Isotropic (ConstantMedium) */
 constexpr int kClasses = 6;
 
-__global__ void __launch_bounds__(256) k_classify(DScene sc, const uint8_t *mat_class, HitBuf hb, const uint32_t *count_in,
-                                                  uint32_t *class_count, uint32_t *class_idx, uint32_t cap) {
-    uint32_t n = *count_in;
+__global__ void __launch_bounds__(256) k_classify(DScene sc, const uint8_t *mat_class, HitBuf hb, WaveCtl *ctl, int cur,
+                                                  uint32_t *class_idx, uint32_t cap) {
+    uint32_t n = ctl->count[cur];
+    uint32_t *class_count = ctl->class_count;
     uint32_t stride = gridDim.x * blockDim.x;
     uint32_t lane = threadIdx.x & 31u;
     for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < n; i0 += stride) {
         uint32_t i = i0 + lane;
         uint32_t cls = 0xffu;
         if (i < n) {
-            uint32_t hop = hb.op[i];
+            uint32_t hop = hb.rec[i].op;
             cls = 0;
             if (hop != RT_NO_HIT) cls = mat_class[load_op_header(unit_ptr(sc.prog, hop & 0x1fffffffu)).z];
         }
@@ -438,52 +508,95 @@ __device__ __forceinline__ bool shade_segment(const DScene &sc, const Ray &r, do
     }
 }
 
+/* where the radiance of a finished path goes */
+struct PathSink {
+    long long *fix;     /* per pixel and channel: sum of contributions in 2^-32 units (exact, order-independent) */
+    double *big;        /* per pixel and channel: contributions too large for the fixed-point sum (|c| >= 2^16) */
+    uint32_t *flags;    /* per pixel: bit c = NaN, bit 3+c = +inf, bit 6+c = -inf seen in channel c */
+    double *cx, *cy, *cz; /* per-path mode (rtgpu_sample_radiance): radiance of path pid, f64 */
+    uint32_t *path_len;   /* per-path mode: segments traced */
+};
+#define RT_FIX_SCALE 4294967296.0 /* 2^32 */
+#define RT_FIX_LIMIT 65536.0      /* |c| below this goes to the fixed-point sum: 32768 samples cannot overflow 63 bits */
+__device__ __forceinline__ void sink_add(const PathSink &sk, uint32_t pixel, int ch, double c) {
+    if (c == 0.) return;
+    if (c != c) {
+        atomicOr(sk.flags + pixel, 1u << ch);
+    } else if (fabs(c) < RT_FIX_LIMIT) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(sk.fix + 3 * (size_t)pixel + ch), (unsigned long long)__double2ll_rn(c * RT_FIX_SCALE));
+    } else if (fabs(c) <= 1.7976931348623157e308) {
+        atomicAdd(sk.big + 3 * (size_t)pixel + ch, c);
+    } else {
+        atomicOr(sk.flags + pixel, (c > 0. ? 8u : 64u) << ch);
+    }
+}
+
 template <int CLS>
-__global__ void __launch_bounds__(kShadeThreads) k_shade(DScene sc, PathQueue qin, HitBuf hb, PathQueue qout, const uint32_t *class_count,
-                                                    const uint32_t *class_idx, uint32_t *count_out, double *cx, double *cy, double *cz,
-                                                    uint32_t *path_len, WaveParams wp, uint32_t bounce, const SortGrid *grid, uint32_t *keys_out) {
-    uint32_t n = class_count[CLS];
+__global__ void __launch_bounds__(kShadeThreads) k_shade(DScene sc, PathQueue qin, HitBuf hb, PathQueue qout, WaveCtl *ctl, int cur,
+                                                    const uint32_t *class_idx, PathSink sk, WaveParams wp, const SortGrid *grid,
+                                                    uint32_t *keys_out) {
+    uint32_t n = ctl->class_count[CLS];
     uint32_t stride = gridDim.x * blockDim.x;
     uint32_t lane = threadIdx.x & 31u;
     for (uint32_t j0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; j0 < n; j0 += stride) {
         uint32_t j = j0 + lane;
-        bool alive = false;
+        bool alive = false, ended = false;
         Ray next;
         V3 beta;
-        uint32_t pid = 0, pos = 0;
+        uint32_t pid = 0, pos = 0, left = 0, traced = 0;
         if (j < n) {
             uint32_t i = class_idx[j];
             Ray r;
             RayRec rr = ld_ray(qin.ray + i);
+            HitRec16 hr = ld_hit(hb.rec + i);
             r.o = v3(rr.ox, rr.oy, rr.oz);
             r.d = v3(rr.dx, rr.dy, rr.dz);
             r.tm = rr.tm;
             beta = ld_beta(qin.st + i);
             pid = rr.pid;
+            left = rr.rng >> RT_POS_BITS; /* segments this path may still trace, this one included */
             rt_rng rng;
-            path_rng(rng, wp, pid, hb.rng[i]);
-            V3 contrib;
-            alive = shade_segment<CLS>(sc, r, hb.t[i], hb.op[i], rng, beta, next, contrib);
+            path_rng(rng, wp, pid, hr.rng);
+            V3 contrib = v3(0., 0., 0.);
+            alive = shade_segment<CLS>(sc, r, hr.t, hr.op, rng, beta, next, contrib);
             pos = rng.pos;
-            if (!alive) {
-                cx[pid] = contrib.x;
-                cy[pid] = contrib.y;
-                cz[pid] = contrib.z;
-                if (path_len) path_len[pid] = bounce + 1;
+            traced = wp.max_depth - left + 1u;
+            if (alive && left <= 1u) { /* depth exhausted: the next ray_color call returns black (main.rs:240-242) */
+                alive = false;
+                contrib = v3(0., 0., 0.);
             }
+            if (!alive) {
+                ended = true;
+                if (sk.cx) {
+                    sk.cx[pid] = contrib.x;
+                    sk.cy[pid] = contrib.y;
+                    sk.cz[pid] = contrib.z;
+                    if (sk.path_len) sk.path_len[pid] = traced;
+                } else {
+                    uint32_t pixel = pid % wp.npix_wave;
+                    sink_add(sk, pixel, 0, contrib.x);
+                    sink_add(sk, pixel, 1, contrib.y);
+                    sink_add(sk, pixel, 2, contrib.z);
+                }
+            }
+        }
+        /* paths by length (rays per bounce follow from it): one atomic per distinct length in the warp */
+        {
+            uint32_t bin = ended ? (traced < RTGPU_MAX_BOUNCE_STATS ? traced : RTGPU_MAX_BOUNCE_STATS) : 0xffffffffu;
+            uint32_t peers = __match_any_sync(0xffffffffu, bin);
+            if (ended && (int)lane == __ffs(peers) - 1) atomicAdd(&ctl->len_hist[bin], (unsigned long long)__popc(peers));
         }
         if constexpr (CLS != 0) {
             /* compaction: one atomic per warp, survivors packed in lane order */
-            __syncwarp();
             uint32_t mask = __ballot_sync(0xffffffffu, alive);
             if (mask) {
                 uint32_t base = 0;
                 int leader = __ffs(mask) - 1;
-                if ((int)lane == leader) base = atomicAdd(count_out, (uint32_t)__popc(mask));
+                if ((int)lane == leader) base = atomicAdd(&ctl->count[cur ^ 1], (uint32_t)__popc(mask));
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (alive) {
                     uint32_t k = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
-                    st_ray(qout.ray + k, next.o, next.d, next.tm, pid, pos);
+                    st_ray(qout.ray + k, next.o, next.d, next.tm, pid, pos | ((left - 1u) << RT_POS_BITS));
                     st_beta(qout.st + k, beta);
                     if (keys_out) keys_out[k] = ray_sort_key(*grid, next.o, next.d);
                 }
@@ -492,23 +605,24 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(DScene sc, PathQueue qi
     }
 }
 
-/* pixel_color += ray_color(...) over the wave's samples, in sample order (main.rs:144-151) */
-__global__ void k_accumulate(const double *cx, const double *cy, const double *cz, float *accum, uint32_t npix, uint32_t nsamples,
-                             int add) {
+/* pixel_color of main.rs:144-151 for the samples of this call: fixed-point sum + large terms, NaN / inf as flagged;
+ * written to (or added to) the caller's float buffer, accumulators cleared for the next call */
+__global__ void k_finish(PathSink sk, float *accum, uint32_t npix, int add) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npix) return;
-    double sx = 0., sy = 0., sz = 0.;
-    for (uint32_t s = 0; s < nsamples; ++s) {
-        size_t k = (size_t)s * npix + p;
-        sx += cx[k];
-        sy += cy[k];
-        sz += cz[k];
-    }
-    float *a = accum + 3 * (size_t)p;
-    if (add) {
-        a[0] += (float)sx; a[1] += (float)sy; a[2] += (float)sz;
-    } else {
-        a[0] = (float)sx; a[1] = (float)sy; a[2] = (float)sz;
+    uint32_t fl = sk.flags[p];
+    sk.flags[p] = 0;
+    for (int c = 0; c < 3; ++c) {
+        size_t k = 3 * (size_t)p + c;
+        double v = (double)sk.fix[k] * (1.0 / RT_FIX_SCALE) + sk.big[k];
+        sk.fix[k] = 0;
+        sk.big[k] = 0.;
+        bool pinf = (fl >> (3 + c)) & 1u, ninf = (fl >> (6 + c)) & 1u;
+        if (((fl >> c) & 1u) || (pinf && ninf)) v = CUDART_NAN;
+        else if (pinf) v = CUDART_INF;
+        else if (ninf) v = -CUDART_INF;
+        float *a = accum + k;
+        *a = add ? *a + (float)v : (float)v;
     }
 }
 
@@ -532,6 +646,7 @@ struct BatchIO {
         pos = 0;
         cur = idx;
     }
+    __device__ __forceinline__ int refill_at() const { return RT_EXTEND_REFILL; }
     __device__ __forceinline__ void prefetch(uint32_t idx) { asm volatile("prefetch.global.L2 [%0];" ::"l"(rays + idx)); }
     __device__ __forceinline__ double draw(uint32_t a, uint32_t b, uint32_t &pos) const {
         rt_rng rng;
@@ -546,16 +661,15 @@ struct BatchIO {
         rng_pos[cur] = pos;
     }
 };
-__global__ void __launch_bounds__(RT_CTA_THREADS, 1) k_trace_extend(DScene sc, const rtgpu_ray *rays, const uint64_t *keys, double *t,
-                                                                   uint32_t *op, uint32_t *rng_pos, uint32_t n, uint32_t *fetch,
-                                                                   PushSave *push_scratch) {
+__global__ void __launch_bounds__(kThreads, RT_EXTEND_MIN_BLOCKS) k_trace_extend(DScene sc, const rtgpu_ray *rays, const uint64_t *keys, double *t,
+                                                                   uint32_t *op, uint32_t *rng_pos, uint32_t n, uint32_t *fetch) {
     BatchIO io;
     io.rays = rays;
     io.keys = keys;
     io.t = t;
     io.op = op;
     io.rng_pos = rng_pos;
-    extend_cta_loop(trav_of(sc), sc.n_units, n, fetch, push_scratch, io);
+    extend_warp_loop(trav_of(sc), sc.n_units, n, fetch, io);
 }
 __global__ void __launch_bounds__(kThreads) k_trace_record(DScene sc, const rtgpu_ray *rays, const double *t, const uint32_t *op,
                                                            const uint32_t *rng_pos, rtgpu_hit *out, uint32_t n) {
@@ -631,36 +745,52 @@ __global__ void k_resolve(const float *accum, int w, int h, int spp, uint8_t *rg
 /* per-device working memory of the wavefront: queues, hit buffer, contributions, counters.  It is
  * independent of the scene, so a destroyed scene parks it for the next scene on the same device
  * (an application that re-creates its scene every frame does not pay cudaMalloc of GBs each time). */
+struct CtlSnapshot { /* what the host reads back, asynchronously, once per iteration */
+    uint32_t count[2], gen_next, fetch;
+};
+constexpr int kSnapRing = 64;
+constexpr int kRunAhead = 2;
 struct WaveRes {
-    size_t cap = 0;
+    size_t cap = 0; /* paths the pool can hold */
     void *wave_mem = nullptr;
     PathQueue q[2];
     HitBuf hb;
-    double *cx = nullptr, *cy = nullptr, *cz = nullptr;
-    uint32_t *path_len = nullptr;
-    uint32_t *class_idx = nullptr;   /* kClasses lists of queue indices, `cap` entries each */
-    uint32_t *class_count = nullptr; /* device: [bounce][8] */
-    uint32_t *counts = nullptr;      /* device: queue length per bounce, then the fetch counters */
-    uint32_t *counts_host = nullptr; /* pinned */
-    int max_counts = 0;
-    float *accum_dev = nullptr;
-    size_t accum_cap = 0;
-    PushSave *push_scratch = nullptr; /* PUSH stacks of the extend kernel's pool slots: one per (CTA, slot, level) */
-    std::vector<cudaEvent_t> events;
-    /* ray reordering: keys written by the shade kernels, their sorted copy, iota and the sorted entry indices */
+    uint32_t *class_idx = nullptr; /* kClasses lists of queue indices, `cap` entries each */
+    /* ray reordering: keys written by k_regen / the shade kernels, their sorted copy, iota and the sorted entry indices */
     uint32_t *sort_keys[2] = {nullptr, nullptr}, *sort_idx[2] = {nullptr, nullptr};
     double *sort_bounds = nullptr; /* 7 moments, then the SortGrid */
     bool iota_ready = false;
     void *sort_temp = nullptr;
     size_t sort_temp_bytes = 0;
+    WaveCtl *ctl = nullptr;           /* device */
+    CtlSnapshot *snap_host = nullptr; /* pinned ring */
+    WaveCtl *ctl_host = nullptr;      /* pinned: final read of the counters */
+    cudaEvent_t snap_ev[kSnapRing] = {};
+    /* pixel sums (PathSink) */
+    void *sink_mem = nullptr;
+    size_t sink_pix = 0;
+    long long *fix = nullptr;
+    double *big = nullptr;
+    uint32_t *flags = nullptr;
+    /* per-path outputs of rtgpu_sample_radiance */
+    void *perpath_mem = nullptr;
+    size_t perpath_cap = 0;
+    double *cx = nullptr, *cy = nullptr, *cz = nullptr;
+    uint32_t *path_len = nullptr;
+    float *accum_dev = nullptr;
+    size_t accum_cap = 0;
+    std::vector<cudaEvent_t> events;
     void release() {
         if (wave_mem) cudaFree(wave_mem);
-        if (counts) cudaFree(counts);
-        if (class_count) cudaFree(class_count);
-        if (counts_host) cudaFreeHost(counts_host);
+        if (sink_mem) cudaFree(sink_mem);
+        if (perpath_mem) cudaFree(perpath_mem);
+        if (ctl) cudaFree(ctl);
+        if (snap_host) cudaFreeHost(snap_host);
+        if (ctl_host) cudaFreeHost(ctl_host);
         if (accum_dev) cudaFree(accum_dev);
-        if (push_scratch) cudaFree(push_scratch);
         if (sort_temp) cudaFree(sort_temp);
+        for (cudaEvent_t e : snap_ev)
+            if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : events) cudaEventDestroy(e);
         *this = WaveRes();
     }
@@ -847,31 +977,23 @@ rtgpu_status SceneArena::commit(rtgpu_scene *s) {
 }
 
 int grid_blocks() { return kSMs * kBlocksPerSM; }
-int extend_blocks() { return kSMs; } /* one persistent 512-thread CTA per SM (extend_cta_loop) */
 
-rtgpu_status ensure_wave(rtgpu_scene *s, size_t n_paths, int max_depth) {
-    if (max_depth + 2 > s->max_counts) {
-        if (s->counts) cudaFree(s->counts);
-        if (s->class_count) cudaFree(s->class_count);
-        if (s->counts_host) cudaFreeHost(s->counts_host);
-        s->counts = nullptr;
-        s->class_count = nullptr;
-        s->counts_host = nullptr;
-        s->max_counts = max_depth + 2;
-        CK(cudaMalloc(&s->counts, 2 * sizeof(uint32_t) * (size_t)s->max_counts)); /* queue lengths, then fetch counters */
-        CK(cudaMallocHost(&s->counts_host, sizeof(uint32_t) * (size_t)s->max_counts));
-        CK(cudaMalloc(&s->class_count, 8 * sizeof(uint32_t) * (size_t)s->max_counts));
+constexpr size_t kBytesPerPath = 2 * (sizeof(RayRec) + sizeof(StateRec)) + sizeof(HitRec16) + 4 * 4 + kClasses * 4; /* 248 */
+
+rtgpu_status ensure_pool(rtgpu_scene *s, size_t n_paths) {
+    if (!s->ctl) {
+        CK(cudaMalloc(&s->ctl, sizeof(WaveCtl)));
+        CK(cudaMallocHost(&s->snap_host, sizeof(CtlSnapshot) * kSnapRing));
+        CK(cudaMallocHost(&s->ctl_host, sizeof(WaveCtl)));
+        for (int i = 0; i < kSnapRing; ++i) CK(cudaEventCreateWithFlags(&s->snap_ev[i], cudaEventDisableTiming));
     }
     if (n_paths <= s->cap) return RTGPU_OK;
     if (s->wave_mem) cudaFree(s->wave_mem);
     s->wave_mem = nullptr;
     s->cap = 0;
     size_t n = (n_paths + 255) & ~(size_t)255;
-    /* per path: 2 queues x (64 B ray + 32 B state) + hit (double + u32 + u32 rng slot) + contrib (3 doubles) + path_len + sort/class lists */
-    size_t bytes = n * (2 * (sizeof(RayRec) + sizeof(StateRec)) + 8 + 4 + 4 + 3 * 8 + 4 + 4 * 4 + kClasses * 4) + 256;
-    CK(cudaMalloc(&s->wave_mem, bytes));
+    CK(cudaMalloc(&s->wave_mem, n * kBytesPerPath + 256));
     char *p = static_cast<char *>(s->wave_mem);
-    auto take_d = [&](double *&dst) { dst = reinterpret_cast<double *>(p); p += n * 8; };
     auto take_u = [&](uint32_t *&dst) { dst = reinterpret_cast<uint32_t *>(p); p += n * 4; };
     for (int k = 0; k < 2; ++k) {
         PathQueue &q = s->q[k];
@@ -880,11 +1002,8 @@ rtgpu_status ensure_wave(rtgpu_scene *s, size_t n_paths, int max_depth) {
         q.st = reinterpret_cast<StateRec *>(p);
         p += n * sizeof(StateRec);
     }
-    take_d(s->hb.t);
-    take_d(s->cx); take_d(s->cy); take_d(s->cz);
-    take_u(s->hb.op);
-    take_u(s->hb.rng);
-    take_u(s->path_len);
+    s->hb.rec = reinterpret_cast<HitRec16 *>(p);
+    p += n * sizeof(HitRec16);
     s->class_idx = reinterpret_cast<uint32_t *>(p);
     p += n * 4 * kClasses;
     take_u(s->sort_keys[0]); take_u(s->sort_keys[1]); take_u(s->sort_idx[0]); take_u(s->sort_idx[1]);
@@ -904,85 +1023,116 @@ rtgpu_status ensure_wave(rtgpu_scene *s, size_t n_paths, int max_depth) {
     s->cap = n;
     return RTGPU_OK;
 }
+rtgpu_status ensure_sink(rtgpu_scene *s, size_t npix, cudaStream_t stream) {
+    if (npix <= s->sink_pix) return RTGPU_OK;
+    if (s->sink_mem) cudaFree(s->sink_mem);
+    s->sink_mem = nullptr;
+    s->sink_pix = 0;
+    size_t bytes = npix * (3 * 8 + 3 * 8 + 4);
+    CK(cudaMalloc(&s->sink_mem, bytes));
+    CK(cudaMemsetAsync(s->sink_mem, 0, bytes, stream)); /* k_finish leaves them cleared from then on */
+    char *p = static_cast<char *>(s->sink_mem);
+    s->fix = reinterpret_cast<long long *>(p);
+    p += npix * 24;
+    s->big = reinterpret_cast<double *>(p);
+    p += npix * 24;
+    s->flags = reinterpret_cast<uint32_t *>(p);
+    s->sink_pix = npix;
+    return RTGPU_OK;
+}
+rtgpu_status ensure_perpath(rtgpu_scene *s, size_t n) {
+    if (n <= s->perpath_cap) return RTGPU_OK;
+    if (s->perpath_mem) cudaFree(s->perpath_mem);
+    s->perpath_mem = nullptr;
+    s->perpath_cap = 0;
+    CK(cudaMalloc(&s->perpath_mem, n * 28));
+    char *p = static_cast<char *>(s->perpath_mem);
+    s->cx = reinterpret_cast<double *>(p);
+    s->cy = s->cx + n;
+    s->cz = s->cy + n;
+    s->path_len = reinterpret_cast<uint32_t *>(s->cz + n);
+    s->perpath_cap = n;
+    return RTGPU_OK;
+}
 
 struct WaveTiming {
     double ms_extend = 0, ms_shade = 0, ms_other = 0;
-    uint64_t launches = 0, launches_extend = 0;
+    uint64_t launches = 0, launches_extend = 0, iterations = 0;
 };
 
-/* Enqueues one whole wave on `stream`; contributions end in s->cx/cy/cz[0 .. n_paths). */
-rtgpu_status run_wave(rtgpu_scene *s, const WaveParams &wp, int max_depth, cudaStream_t stream, bool want_len, bool timing,
-                      WaveTiming *wt, uint64_t *rays, uint64_t *rays_per_bounce) {
-    rtgpu_status st = ensure_wave(s, wp.n_paths, max_depth);
+/* Traces wp.n_paths paths with at most wp.pool of them in flight; radiance goes to `sk`.  Everything is enqueued on
+ * `stream`; the host only looks at asynchronous snapshots of the control block to know when to stop. */
+rtgpu_status run_paths(rtgpu_scene *s, const WaveParams &wp, const PathSink &sk, cudaStream_t stream, bool timing, WaveTiming *wt,
+                       uint64_t *rays, uint64_t *rays_per_bounce) {
+    rtgpu_status st = ensure_pool(s, wp.pool);
     if (st != RTGPU_OK) return st;
-    size_t n = wp.n_paths;
-    CK(cudaMemsetAsync(s->counts, 0, 2 * sizeof(uint32_t) * (size_t)s->max_counts, stream));
-    CK(cudaMemsetAsync(s->class_count, 0, 8 * sizeof(uint32_t) * (size_t)s->max_counts, stream));
-    CK(cudaMemcpyAsync(s->counts, &wp.n_paths, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-    CK(cudaMemsetAsync(s->cx, 0, n * 8, stream));
-    CK(cudaMemsetAsync(s->cy, 0, n * 8, stream));
-    CK(cudaMemsetAsync(s->cz, 0, n * 8, stream));
-    if (want_len) CK(cudaMemsetAsync(s->path_len, 0, n * 4, stream));
-    size_t n_ev = timing ? (size_t)(3 * max_depth + 2) : 0;
-    while (s->events.size() < n_ev) {
-        cudaEvent_t e;
-        CK(cudaEventCreate(&e));
-        s->events.push_back(e);
-    }
-    int blocks = grid_blocks();
-    size_t ev = 0;
-    if (timing) CK(cudaEventRecord(s->events[ev++], stream));
-    k_raygen<<<blocks, kThreads, 0, stream>>>(s->d, s->q[0], wp);
-    if (timing) CK(cudaEventRecord(s->events[ev++], stream));
-    int cur = 0; /* queue that holds the rays of the current bounce */
-    int bounces_run = 0;
-    /* bounce rays are sorted (see "ray reordering") while a bounce carries at least sort_min of them */
-    bool sorting = s->sort_mode != 0 && wp.n_paths >= s->sort_min && max_depth > 1;
+    if (wp.n_paths == 0 || wp.max_depth == 0) return RTGPU_OK; /* depth 0: every ray_color call returns black (main.rs:240-242) */
+    CK(cudaMemsetAsync(s->ctl, 0, sizeof(WaveCtl), stream));
+    const int blocks = grid_blocks();
+    const uint32_t cap = (uint32_t)s->cap;
+    bool sorting = s->sort_mode != 0 && wp.n_paths >= s->sort_min && wp.max_depth > 1;
     SortGrid *grid = reinterpret_cast<SortGrid *>(s->sort_bounds + 8);
     if (sorting && !s->iota_ready) {
-        k_iota<<<blocks, 256, 0, stream>>>(s->sort_idx[0], (uint32_t)s->cap);
+        k_iota<<<blocks, 256, 0, stream>>>(s->sort_idx[0], cap);
         s->iota_ready = true;
     }
-    for (int b = 0; b < max_depth; ++b) {
-        const uint32_t *perm = nullptr;
-        if (sorting && b >= 1) {
-            /* the queue length is needed on the host to size the sort: one 4-byte readback per sorted bounce */
-            CK(cudaMemcpyAsync(s->counts_host + b, s->counts + b, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-            CK(cudaStreamSynchronize(stream));
-            uint32_t nb = s->counts_host[b];
-            if (nb == 0) break;
-            if (nb >= s->sort_min) {
-                size_t tb = s->sort_temp_bytes;
-                CK(cub::DeviceRadixSort::SortPairs(s->sort_temp, tb, s->sort_keys[0], s->sort_keys[1], s->sort_idx[0], s->sort_idx[1],
-                                                   (int)nb, 0, kSortKeyBits, stream));
-                perm = s->sort_idx[1]; /* (the library's sort kernels are not counted in stats->launches: those are this file's) */
-            } else {
-                sorting = false; /* queues only shrink: the rest of the wave runs in arrival order */
-            }
-        } else if (b > 0 && (b % 8) == 0) {
-            /* every 8 bounces: is anything still alive? (one 4-byte readback) */
-            CK(cudaMemcpyAsync(s->counts_host + b, s->counts + b, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-            CK(cudaStreamSynchronize(stream));
-            if (s->counts_host[b] == 0) break;
+    if (sorting) { /* until the first hit points are known every key is 0 (the first iteration is camera rays in pixel order) */
+        CK(cudaMemsetAsync(grid, 0, sizeof(SortGrid), stream));
+    }
+    size_t ev = 0;
+    auto mark = [&]() -> rtgpu_status {
+        if (!timing) return RTGPU_OK;
+        if (ev == s->events.size()) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            s->events.push_back(e);
         }
+        CK(cudaEventRecord(s->events[ev++], stream));
+        return RTGPU_OK;
+    };
+    /* upper bound of the number of survivors that enter the coming iteration, as far as the host knows */
+    uint32_t bound = wp.pool < wp.n_paths ? wp.pool : wp.n_paths;
+    bool gen_done = false; /* host knows that every path has been generated */
+    const uint64_t max_iter = (uint64_t)wp.n_paths / (bound ? bound : 1) * (uint64_t)wp.max_depth + 2ull * wp.max_depth + 64;
+    int cur = 0;
+    uint64_t it = 0, seen = 0;
+    bool finished = false;
+    std::vector<int> phase_of_event; /* 0 other, 1 extend, 2 shade: what ran between event k and k+1 */
+    for (; it < max_iter && !finished; ++it) {
         PathQueue &qin = s->q[cur], &qout = s->q[cur ^ 1];
-        if (timing) CK(cudaEventRecord(s->events[ev++], stream));
-        k_extend<<<extend_blocks(), RT_CTA_THREADS, sizeof(PoolShared), stream>>>(s->d, qin, s->hb, s->counts + b, s->counts + s->max_counts + b, wp, perm, s->push_scratch);
+        if ((st = mark()) != RTGPU_OK) return st;
+        k_iter_begin<<<1, 32, 0, stream>>>(s->ctl, cur);
+        if (!gen_done) {
+            k_regen<<<blocks, kThreads, 0, stream>>>(s->d, qin, s->ctl, cur, wp);
+            if (wt) wt->launches += 1;
+        }
+        k_regen_commit<<<1, 1, 0, stream>>>(s->ctl, cur, wp);
+        const uint32_t *perm = nullptr;
+        if (sorting && it >= 1 && bound >= s->sort_min) {
+            k_pad_keys<<<blocks, 256, 0, stream>>>(s->ctl, s->sort_keys[0], bound);
+            size_t tb = s->sort_temp_bytes;
+            CK(cub::DeviceRadixSort::SortPairs(s->sort_temp, tb, s->sort_keys[0], s->sort_keys[1], s->sort_idx[0], s->sort_idx[1], (int)bound, 0,
+                                               kSortKeyBits, stream));
+            perm = s->sort_idx[1]; /* (the library's sort kernels are not counted in stats->launches: those are this file's) */
+            if (wt) wt->launches += 1;
+        }
+        phase_of_event.push_back(0);
+        if ((st = mark()) != RTGPU_OK) return st;
+        k_extend<<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->ctl, cur, wp, perm, bound);
         CK(cudaGetLastError()); /* a failed extend launch must not let the shade kernels read stale hits */
-        if (timing) CK(cudaEventRecord(s->events[ev++], stream));
-        if (sorting && b == 0) { /* the origin grid of this wave's keys, from the first hit points */
+        phase_of_event.push_back(1);
+        if ((st = mark()) != RTGPU_OK) return st;
+        if (sorting && it == 0) { /* the origin grid of this render's keys, from the first hit points */
             CK(cudaMemsetAsync(s->sort_bounds, 0, 7 * sizeof(double), stream));
-            k_sort_moments<<<blocks, kThreads, 0, stream>>>(qin, s->hb, s->counts + b, s->sort_bounds);
+            k_sort_moments<<<blocks, kThreads, 0, stream>>>(qin, s->hb, s->ctl, cur, s->sort_bounds);
             k_sort_grid<<<1, 1, 0, stream>>>(s->sort_bounds, grid);
             if (wt) wt->launches += 2;
         }
         {
-            uint32_t *cc = s->class_count + 8 * b;
-            uint32_t *pl = want_len ? s->path_len : nullptr;
-            uint32_t cap = (uint32_t)s->cap;
-            k_classify<<<blocks, 256, 0, stream>>>(s->d, s->mat_class, s->hb, s->counts + b, cc, s->class_idx, cap);
-#define RT_SHADE(C) k_shade<C><<<kSMs * RT_SHADE_BLOCKS_PER_SM, kShadeThreads, 0, stream>>>(s->d, qin, s->hb, qout, cc, s->class_idx + (size_t)C * cap, s->counts + b + 1, \
-                                                                s->cx, s->cy, s->cz, pl, wp, (uint32_t)b, grid, sorting ? s->sort_keys[0] : nullptr)
+            k_classify<<<blocks, 256, 0, stream>>>(s->d, s->mat_class, s->hb, s->ctl, cur, s->class_idx, cap);
+#define RT_SHADE(C)                                                                                                                     \
+    k_shade<C><<<kSMs * RT_SHADE_BLOCKS_PER_SM, kShadeThreads, 0, stream>>>(s->d, qin, s->hb, qout, s->ctl, cur, s->class_idx + (size_t)C * cap, sk, \
+                                                                            wp, grid, sorting ? s->sort_keys[0] : nullptr)
             int n_launched = 0;
             RT_SHADE(0);
             if (s->class_present[1]) { RT_SHADE(1); ++n_launched; }
@@ -990,45 +1140,65 @@ rtgpu_status run_wave(rtgpu_scene *s, const WaveParams &wp, int max_depth, cudaS
             if (s->class_present[3]) { RT_SHADE(3); ++n_launched; }
             if (s->class_present[4]) { RT_SHADE(4); ++n_launched; }
             if (s->class_present[5]) { RT_SHADE(5); ++n_launched; }
-            if (wt) wt->launches += 2 + (uint64_t)n_launched; /* classify + class 0 + the others */
+            if (wt) wt->launches += 5 + (uint64_t)n_launched; /* iter_begin, commit, extend, classify, class 0 + the others */
 #undef RT_SHADE
         }
-        if (timing) CK(cudaEventRecord(s->events[ev++], stream));
+        phase_of_event.push_back(2);
+        /* snapshot of the control block: tells the host, a few iterations late, how many paths are left */
+        const int slot = (int)(it % kSnapRing);
+        CK(cudaMemcpyAsync(s->snap_host + slot, s->ctl, sizeof(CtlSnapshot), cudaMemcpyDeviceToHost, stream));
+        CK(cudaEventRecord(s->snap_ev[slot], stream));
         cur ^= 1;
-        ++bounces_run;
-    }
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(s->counts_host, s->counts, sizeof(uint32_t) * (size_t)(max_depth + 1), cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
-    for (int b = 0; b < bounces_run; ++b) {
-        *rays += s->counts_host[b];
-        if (rays_per_bounce && b < RTGPU_MAX_BOUNCE_STATS) rays_per_bounce[b] += s->counts_host[b];
+        /* consume the snapshots that have arrived (never waits, except when the ring is about to wrap) */
+        while (seen <= it) {
+            const int sl = (int)(seen % kSnapRing);
+            /* the host stays at most kRunAhead iterations ahead of the device: the queue bound it sizes the sort with stays
+             * fresh and a finished render is not followed by a long tail of empty launches; the device always has work queued */
+            cudaError_t q = (it - seen >= (uint64_t)kRunAhead) ? cudaEventSynchronize(s->snap_ev[sl]) : cudaEventQuery(s->snap_ev[sl]);
+            if (q == cudaErrorNotReady) break;
+            CK(q);
+            const CtlSnapshot &sn = s->snap_host[sl];
+            const int next_q = (int)((seen + 1) & 1); /* queue filled by the shade kernels of iteration `seen` */
+            const uint32_t survivors = sn.count[next_q], left = wp.n_paths - sn.gen_next;
+            gen_done = left == 0;
+            /* How many survivors will the coming iterations carry?  Never more than what is alive now plus what can still be
+             * generated; in the steady state of a regenerating pool about what the last known iteration carried.  This only
+             * sizes the sort: survivors beyond it are walked in place, like the new camera rays, and the result is the same. */
+            uint64_t b2 = (uint64_t)survivors + left;
+            if (b2 > wp.pool) b2 = wp.pool;
+            uint64_t est = (uint64_t)survivors + survivors / 16 + 1024;
+            bound = (uint32_t)(est < b2 ? est : b2);
+            if (gen_done && survivors == 0) finished = true;
+            ++seen;
+        }
     }
     if (wt) {
-        wt->launches += 1 + (uint64_t)bounces_run; /* raygen + extends; shade launches counted in the loop */
-        wt->launches_extend += (uint64_t)bounces_run;
-        if (timing) {
+        wt->launches_extend += it;
+        wt->iterations += it;
+    }
+    CK(cudaGetLastError());
+    if ((st = mark()) != RTGPU_OK) return st;
+    CK(cudaMemcpyAsync(s->ctl_host, s->ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    const WaveCtl &c = *s->ctl_host;
+    if (c.gen_next != wp.n_paths || c.count[cur] != 0) {
+        g_err = "render did not finish within its iteration budget";
+        return RTGPU_ERR_CUDA;
+    }
+    *rays += c.rays;
+    if (rays_per_bounce) {
+        /* rays of bounce b = paths that traced more than b segments */
+        unsigned long long longer = 0;
+        for (int L = RTGPU_MAX_BOUNCE_STATS; L >= 1; --L) {
+            longer += c.len_hist[L];
+            rays_per_bounce[L - 1] += longer;
+        }
+    }
+    if (wt && timing) {
+        for (size_t k = 0; k + 1 < ev && k < phase_of_event.size(); ++k) {
             float ms = 0;
-            CK(cudaEventElapsedTime(&ms, s->events[0], s->events[1]));
-            wt->ms_other += ms;
-            const bool trace = getenv("RTGPU_TRACE_BOUNCES") != nullptr; /* per-bounce table on stderr (tuning aid) */
-            for (int b = 0; b < bounces_run; ++b) {
-                if (trace) {
-                    float me = 0, ms2 = 0;
-                    cudaEventElapsedTime(&me, s->events[2 + 3 * b], s->events[3 + 3 * b]);
-                    cudaEventElapsedTime(&ms2, s->events[3 + 3 * b], s->events[4 + 3 * b]);
-                    fprintf(stderr, "bounce %2d rays %9u extend %8.3f ms (%7.1f Mrays/s) shade %8.3f ms\n", b, s->counts_host[b], me,
-                            s->counts_host[b] / (me * 1e3 + 1e-9), ms2);
-                }
-                if (b > 0) { /* sort between the previous shade and this extend */
-                    CK(cudaEventElapsedTime(&ms, s->events[1 + 3 * b], s->events[2 + 3 * b]));
-                    wt->ms_other += ms;
-                }
-                CK(cudaEventElapsedTime(&ms, s->events[2 + 3 * b], s->events[3 + 3 * b]));
-                wt->ms_extend += ms;
-                CK(cudaEventElapsedTime(&ms, s->events[3 + 3 * b], s->events[4 + 3 * b]));
-                wt->ms_shade += ms;
-            }
+            CK(cudaEventElapsedTime(&ms, s->events[k], s->events[k + 1]));
+            (phase_of_event[k] == 1 ? wt->ms_extend : phase_of_event[k] == 2 ? wt->ms_shade : wt->ms_other) += ms;
         }
     }
     return RTGPU_OK;
@@ -1137,9 +1307,6 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
     s->d.n_lights = desc->n_lights;
     s->d.cam = desc->camera;
     for (int c = 0; c < 3; ++c) s->d.background[c] = desc->background[c];
-    if (!s->push_scratch) CK(cudaMalloc(&s->push_scratch, sizeof(PushSave) * (size_t)extend_blocks() * RT_POOL_RAYS * RT_MAX_PUSH));
-    CK(cudaFuncSetAttribute(k_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoolShared)));
-    CK(cudaFuncSetAttribute(k_trace_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoolShared)));
     *out = s;
     return RTGPU_OK;
 }
@@ -1162,13 +1329,23 @@ rtgpu_status rtgpu_scene_destroy(rtgpu_scene *s) {
     return RTGPU_OK;
 }
 
+namespace {
+struct EventPair { /* destroyed on every exit path */
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() {
+        if (a) cudaEventDestroy(a);
+        if (b) cudaEventDestroy(b);
+    }
+};
+} // namespace
+
 rtgpu_status rtgpu_render(rtgpu_scene *s, const rtgpu_render_params *p, float *accum, rtgpu_stats *stats) {
     if (!s || !p || !accum) {
         g_err = "NULL argument";
         return RTGPU_ERR_INVALID_ARG;
     }
-    if (p->width < 2 || p->height < 2 || p->spp_end < p->spp_begin || p->max_depth < 0 || p->max_depth > 4096) {
-        g_err = "bad render parameters (width/height >= 2: u = (x+xi)/(W-1), main.rs:147)";
+    if (p->width < 2 || p->height < 2 || p->spp_end < p->spp_begin || p->max_depth < 0 || p->max_depth > 4095) {
+        g_err = "bad render parameters (width/height >= 2: u = (x+xi)/(W-1), main.rs:147; max_depth <= 4095)";
         return RTGPU_ERR_INVALID_ARG;
     }
     if (!(s->d.cam.time0 < s->d.cam.time1)) {
@@ -1182,24 +1359,14 @@ rtgpu_status rtgpu_render(rtgpu_scene *s, const rtgpu_render_params *p, float *a
         g_err = "image too large";
         return RTGPU_ERR_INVALID_ARG;
     }
-    size_t max_paths = p->max_paths_in_flight > 0 ? (size_t)p->max_paths_in_flight : ((size_t)1 << 24);
-    if (p->max_paths_in_flight <= 0) {
-        /* default wave: larger waves are faster (deep bounces launch with more rays, sorted rays are closer neighbours), so a
-         * caller who does not say takes a quarter of the free device memory at 276 B per path, between 2^24 and 2^27 paths;
-         * the working memory this render already holds counts as free */
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            size_t paths = (free_b / 4 + s->cap * 276) / 276;
-            if (paths > ((size_t)1 << 27)) paths = (size_t)1 << 27;
-            if (paths > max_paths) max_paths = paths;
-        } else {
-            cudaGetLastError();
-        }
-    }
-    if (max_paths < npix) max_paths = npix;
-    if (max_paths > 0xfffffff0u) max_paths = 0xfffffff0u;
-    int spp_per_wave = (int)(max_paths / npix);
-    if (spp_per_wave < 1) spp_per_wave = 1;
+    /* paths kept in flight: the caller's cap, else 12 Mi (3.1 GB of pool at 248 B per path); never more than the job */
+    size_t pool = p->max_paths_in_flight > 0 ? (size_t)p->max_paths_in_flight : ((size_t)12 << 20);
+    if (pool < 4096) pool = 4096;
+    if (pool > 0x7ffffff0u) pool = 0x7ffffff0u;
+    /* one pass covers at most 32768 samples per pixel (the fixed-point pixel sums cannot overflow) and < 2^32 paths */
+    size_t spp_per_pass = 0xfffffff0u / npix;
+    if (spp_per_pass > 32768) spp_per_pass = 32768;
+    if (spp_per_pass < 1) spp_per_pass = 1;
 
     float *acc_dev = accum;
     if (!p->accum_on_device) {
@@ -1213,18 +1380,25 @@ rtgpu_status rtgpu_render(rtgpu_scene *s, const rtgpu_render_params *p, float *a
         acc_dev = s->accum_dev;
         if (p->accumulate) CK(cudaMemcpyAsync(acc_dev, accum, npix * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
     }
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    CK(cudaEventRecord(e0, stream));
+    rtgpu_status st = ensure_sink(s, npix, stream);
+    if (st != RTGPU_OK) return st;
+    EventPair ev;
+    CK(cudaEventCreate(&ev.a));
+    CK(cudaEventCreate(&ev.b));
+    CK(cudaEventRecord(ev.a, stream));
     WaveTiming wt;
     uint64_t rays = 0;
     uint64_t per_bounce[RTGPU_MAX_BOUNCE_STATS];
     memset(per_bounce, 0, sizeof per_bounce);
+    PathSink sk;
+    memset(&sk, 0, sizeof sk);
+    sk.fix = s->fix;
+    sk.big = s->big;
+    sk.flags = s->flags;
     bool first = true;
     if (p->spp_end == p->spp_begin && !p->accumulate) CK(cudaMemsetAsync(acc_dev, 0, npix * 3 * sizeof(float), stream));
-    for (int sb = p->spp_begin; sb < p->spp_end; sb += spp_per_wave) {
-        int ns = p->spp_end - sb < spp_per_wave ? p->spp_end - sb : spp_per_wave;
+    for (int64_t sb = p->spp_begin; sb < p->spp_end; sb += (int64_t)spp_per_pass) {
+        int64_t ns = p->spp_end - sb < (int64_t)spp_per_pass ? p->spp_end - sb : (int64_t)spp_per_pass;
         WaveParams wp;
         wp.seed = p->seed;
         wp.first_pixel = 0;
@@ -1233,21 +1407,20 @@ rtgpu_status rtgpu_render(rtgpu_scene *s, const rtgpu_render_params *p, float *a
         wp.n_paths = (uint32_t)(npix * (size_t)ns);
         wp.width = p->width;
         wp.height = p->height;
-        rtgpu_status st = run_wave(s, wp, p->max_depth, stream, false, stats != nullptr, &wt, &rays, per_bounce);
+        wp.max_depth = (uint32_t)p->max_depth;
+        wp.pool = (uint32_t)(pool < wp.n_paths ? pool : wp.n_paths);
+        st = run_paths(s, wp, sk, stream, stats != nullptr, &wt, &rays, per_bounce);
         if (st != RTGPU_OK) return st;
-        k_accumulate<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(s->cx, s->cy, s->cz, acc_dev, (uint32_t)npix, (uint32_t)ns,
-                                                                          (first && !p->accumulate) ? 0 : 1);
+        k_finish<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(sk, acc_dev, (uint32_t)npix, (first && !p->accumulate) ? 0 : 1);
         wt.launches += 1;
         first = false;
     }
     CK(cudaGetLastError());
     if (!p->accum_on_device) CK(cudaMemcpyAsync(accum, acc_dev, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, stream));
-    CK(cudaEventRecord(e1, stream));
+    CK(cudaEventRecord(ev.b, stream));
     CK(cudaStreamSynchronize(stream));
     float ms = 0;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    CK(cudaEventElapsedTime(&ms, ev.a, ev.b));
     if (stats) {
         memset(stats, 0, sizeof *stats);
         stats->rays = rays;
@@ -1258,6 +1431,8 @@ rtgpu_status rtgpu_render(rtgpu_scene *s, const rtgpu_render_params *p, float *a
         stats->ms_other = wt.ms_other;
         stats->launches = wt.launches;
         stats->launches_extend = wt.launches_extend;
+        stats->pool_paths = s->cap;
+        stats->pool_bytes = s->cap * kBytesPerPath + s->sink_pix * 52;
         memcpy(stats->rays_per_bounce, per_bounce, sizeof per_bounce);
     }
     return RTGPU_OK;
@@ -1297,7 +1472,7 @@ rtgpu_status rtgpu_trace_batch(rtgpu_scene *s, const rtgpu_ray *rays, int64_t n,
         CK(cudaEventCreate(&e0));
         CK(cudaEventCreate(&e1));
         CK(cudaEventRecord(e0, 0));
-        k_trace_extend<<<extend_blocks(), RT_CTA_THREADS, sizeof(PoolShared)>>>(s->d, d_rays, d_keys, d_t, d_u32, d_u32 + n, (uint32_t)n, d_u32 + 2 * n, s->push_scratch);
+        k_trace_extend<<<grid_blocks(), kThreads>>>(s->d, d_rays, d_keys, d_t, d_u32, d_u32 + n, (uint32_t)n, d_u32 + 2 * n);
         CK(cudaEventRecord(e1, 0));
         k_trace_record<<<grid_blocks(), kThreads>>>(s->d, d_rays, d_t, d_u32, d_u32 + n, d_out, (uint32_t)n);
         CK(cudaGetLastError());
@@ -1353,12 +1528,14 @@ rtgpu_status rtgpu_camera_rays(rtgpu_scene *s, int32_t width, int32_t height, in
 
 rtgpu_status rtgpu_sample_radiance(rtgpu_scene *s, int32_t width, int32_t height, int64_t first_pixel, int64_t n, int32_t k,
                                    int32_t max_depth, uint64_t seed, double *out_rgb, uint32_t *out_rays) {
-    if (!s || !out_rgb || n <= 0 || width < 2 || height < 2 || first_pixel < 0 || first_pixel + n > (int64_t)width * height ||
-        max_depth < 0 || max_depth > 4096) {
+    if (!s || !out_rgb || n <= 0 || n > 0x7fffff00 || width < 2 || height < 2 || first_pixel < 0 ||
+        first_pixel + n > (int64_t)width * height || max_depth < 0 || max_depth > 4095) {
         g_err = "bad argument";
         return RTGPU_ERR_INVALID_ARG;
     }
     CK(cudaSetDevice(s->device));
+    rtgpu_status st = ensure_perpath(s, (size_t)n);
+    if (st != RTGPU_OK) return st;
     WaveParams wp;
     wp.seed = seed;
     wp.first_pixel = (uint32_t)first_pixel;
@@ -1367,8 +1544,17 @@ rtgpu_status rtgpu_sample_radiance(rtgpu_scene *s, int32_t width, int32_t height
     wp.n_paths = (uint32_t)n;
     wp.width = width;
     wp.height = height;
+    wp.max_depth = (uint32_t)max_depth;
+    wp.pool = (uint32_t)(n < 4096 ? 4096 : n);
+    PathSink sk;
+    memset(&sk, 0, sizeof sk);
+    sk.cx = s->cx;
+    sk.cy = s->cy;
+    sk.cz = s->cz;
+    sk.path_len = s->path_len;
+    CK(cudaMemsetAsync(s->perpath_mem, 0, (size_t)s->perpath_cap * 28, 0));
     uint64_t rays = 0;
-    rtgpu_status st = run_wave(s, wp, max_depth, 0, true, false, nullptr, &rays, nullptr);
+    st = run_paths(s, wp, sk, 0, false, nullptr, &rays, nullptr);
     if (st != RTGPU_OK) return st;
     std::vector<double> tmp((size_t)n * 3);
     CK(cudaMemcpy(tmp.data(), s->cx, (size_t)n * 8, cudaMemcpyDeviceToHost));
@@ -1379,11 +1565,7 @@ rtgpu_status rtgpu_sample_radiance(rtgpu_scene *s, int32_t width, int32_t height
         out_rgb[3 * i + 1] = tmp[(size_t)(n + i)];
         out_rgb[3 * i + 2] = tmp[(size_t)(2 * n + i)];
     }
-    if (out_rays) {
-        CK(cudaMemcpy(out_rays, s->path_len, (size_t)n * 4, cudaMemcpyDeviceToHost));
-        for (int64_t i = 0; i < n; ++i)
-            if (out_rays[i] == 0) out_rays[i] = (uint32_t)max_depth; /* still alive after max_depth segments */
-    }
+    if (out_rays) CK(cudaMemcpy(out_rays, s->path_len, (size_t)n * 4, cudaMemcpyDeviceToHost));
     return RTGPU_OK;
 }
 
@@ -1412,6 +1594,179 @@ rtgpu_status rtgpu_resolve(const float *accum, int32_t width, int32_t height, in
     if (d_acc) cudaFree(d_acc);
     if (d_rgb) cudaFree(d_rgb);
     return st;
+}
+
+
+/* ---- spp sharding over the GPUs of one box -----------------------------------------------------------------------
+ * Samples of a pixel are i.i.d. and the reference already sums them (main.rs:144-151): device g of G renders ALL pixels
+ * for sample indices [b + g*n/G, b + (g+1)*n/G), one host thread per device as upstream has one per scanline block
+ * (main.rs:109-162), and the per-device float sums meet in ONE ncclReduce(sum) on the first device (main.rs:171-183).
+ * NCCL is looked up at run time (dlopen): librtgpu.so carries no link-time dependency on it, and a process that has
+ * already loaded a libnccl.so.2 (PyTorch) shares that copy. */
+} // extern "C"
+
+#include <dlfcn.h>
+
+#include <thread>
+
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    int (*CommInitAll)(void **, int, const int *) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Reduce)(const void *, void *, size_t, int, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (lib) return true;
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) return false;
+        CommInitAll = reinterpret_cast<decltype(CommInitAll)>(dlsym(lib, "ncclCommInitAll"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+        GroupStart = reinterpret_cast<decltype(GroupStart)>(dlsym(lib, "ncclGroupStart"));
+        GroupEnd = reinterpret_cast<decltype(GroupEnd)>(dlsym(lib, "ncclGroupEnd"));
+        Reduce = reinterpret_cast<decltype(Reduce)>(dlsym(lib, "ncclReduce"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+        return CommInitAll && CommDestroy && GroupStart && GroupEnd && Reduce;
+    }
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mutex;
+constexpr int kNcclFloat32 = 7, kNcclSum = 0; /* ncclDataType_t / ncclRedOp_t values of nccl.h (stable since NCCL 2.0) */
+} // namespace
+
+extern "C" {
+
+rtgpu_status rtgpu_multi_render(const rtgpu_scene_desc *desc, const rtgpu_render_params *params, int32_t n_devices,
+                                const int32_t *devices, float *accum_root, rtgpu_stats *stats, double *ms_reduce) {
+    if (!desc || !params || !accum_root || n_devices < 1 || n_devices > kMaxDevices) {
+        g_err = "bad argument";
+        return RTGPU_ERR_INVALID_ARG;
+    }
+    if (params->spp_end < params->spp_begin || params->accumulate || params->accum_on_device) {
+        g_err = "rtgpu_multi_render writes host memory and does not accumulate";
+        return RTGPU_ERR_INVALID_ARG;
+    }
+    int have = rtgpu_device_count();
+    std::vector<int> devs((size_t)n_devices);
+    for (int g = 0; g < n_devices; ++g) {
+        devs[g] = devices ? devices[g] : g;
+        if (devs[g] < 0 || devs[g] >= have) {
+            g_err = "device ordinal out of range";
+            return RTGPU_ERR_INVALID_ARG;
+        }
+    }
+    const size_t n_float = (size_t)3 * (size_t)params->width * (size_t)params->height;
+    std::vector<void *> comms((size_t)n_devices, nullptr);
+    if (n_devices > 1) {
+        std::lock_guard<std::mutex> lock(g_nccl_mutex);
+        if (!g_nccl.load()) {
+            g_err = "libnccl.so.2 not found: rtgpu_multi_render needs NCCL for more than one device";
+            return RTGPU_ERR_NCCL;
+        }
+        int rc = g_nccl.CommInitAll(comms.data(), n_devices, devs.data());
+        if (rc != 0) {
+            g_err = std::string("ncclCommInitAll: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "failed");
+            return RTGPU_ERR_NCCL;
+        }
+    }
+    std::vector<float *> accum((size_t)n_devices, nullptr);
+    std::vector<rtgpu_scene *> scenes((size_t)n_devices, nullptr);
+    std::vector<rtgpu_stats> st((size_t)n_devices);
+    std::vector<rtgpu_status> rc((size_t)n_devices, RTGPU_OK);
+    std::vector<std::string> msg((size_t)n_devices);
+    const long long n_spp = (long long)params->spp_end - params->spp_begin;
+    {
+        std::vector<std::thread> pool;
+        for (int g = 0; g < n_devices; ++g)
+            pool.emplace_back([&, g]() {
+                auto fail = [&](rtgpu_status code) {
+                    rc[g] = code;
+                    msg[g] = rtgpu_last_error(); /* this thread's message */
+                };
+                if (cudaSetDevice(devs[g]) != cudaSuccess) {
+                    g_err = "cudaSetDevice failed";
+                    return fail(RTGPU_ERR_CUDA);
+                }
+                rtgpu_status r = rtgpu_scene_create(desc, devs[g], &scenes[g]);
+                if (r != RTGPU_OK) return fail(r);
+                if (cudaMalloc(&accum[g], n_float * sizeof(float)) != cudaSuccess) {
+                    g_err = "out of device memory";
+                    return fail(RTGPU_ERR_OOM);
+                }
+                rtgpu_render_params p = *params;
+                p.spp_begin = params->spp_begin + (int32_t)(g * n_spp / n_devices);
+                p.spp_end = params->spp_begin + (int32_t)((g + 1) * n_spp / n_devices);
+                p.device = devs[g];
+                p.stream = nullptr;
+                p.accum_on_device = 1;
+                p.accumulate = 0;
+                r = rtgpu_render(scenes[g], &p, accum[g], &st[g]);
+                if (r != RTGPU_OK) return fail(r);
+            });
+        for (auto &t : pool) t.join();
+    }
+    rtgpu_status result = RTGPU_OK;
+    for (int g = 0; g < n_devices && result == RTGPU_OK; ++g)
+        if (rc[g] != RTGPU_OK) {
+            result = rc[g];
+            g_err = "device " + std::to_string(devs[g]) + ": " + msg[g];
+        }
+    double red_ms = 0.;
+    if (result == RTGPU_OK && n_devices > 1) {
+        auto t0 = std::chrono::steady_clock::now();
+        int nrc = g_nccl.GroupStart();
+        for (int g = 0; g < n_devices && nrc == 0; ++g) {
+            cudaSetDevice(devs[g]);
+            nrc = g_nccl.Reduce(accum[g], accum[g], n_float, kNcclFloat32, kNcclSum, 0, comms[g], (cudaStream_t)0);
+        }
+        int erc = g_nccl.GroupEnd();
+        if (nrc == 0) nrc = erc;
+        for (int g = 0; g < n_devices; ++g) {
+            cudaSetDevice(devs[g]);
+            if (cudaStreamSynchronize(0) != cudaSuccess && nrc == 0) nrc = -1;
+        }
+        red_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (nrc != 0) {
+            g_err = std::string("ncclReduce: ") + (nrc > 0 && g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "failed");
+            result = RTGPU_ERR_NCCL;
+        }
+    }
+    if (result == RTGPU_OK) {
+        cudaSetDevice(devs[0]);
+        if (cudaMemcpy(accum_root, accum[0], n_float * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            g_err = "copy of the reduced image failed";
+            result = RTGPU_ERR_CUDA;
+        }
+    }
+    for (int g = 0; g < n_devices; ++g) {
+        cudaSetDevice(devs[g]);
+        if (accum[g]) cudaFree(accum[g]);
+        if (scenes[g]) rtgpu_scene_destroy(scenes[g]);
+        if (comms[g]) g_nccl.CommDestroy(comms[g]);
+    }
+    if (result == RTGPU_OK && stats) {
+        memset(stats, 0, sizeof *stats);
+        for (int g = 0; g < n_devices; ++g) {
+            stats->rays += st[g].rays;
+            stats->samples += st[g].samples;
+            stats->launches += st[g].launches;
+            stats->launches_extend += st[g].launches_extend;
+            stats->ms_extend += st[g].ms_extend;
+            stats->ms_shade += st[g].ms_shade;
+            stats->ms_other += st[g].ms_other;
+            if (st[g].ms_total > stats->ms_total) stats->ms_total = st[g].ms_total; /* the slowest device */
+            if (st[g].pool_paths > stats->pool_paths) stats->pool_paths = st[g].pool_paths;
+            if (st[g].pool_bytes > stats->pool_bytes) stats->pool_bytes = st[g].pool_bytes;
+            for (int b = 0; b < RTGPU_MAX_BOUNCE_STATS; ++b) stats->rays_per_bounce[b] += st[g].rays_per_bounce[b];
+        }
+    }
+    if (ms_reduce) *ms_reduce = red_ms;
+    return result;
 }
 
 } // extern "C"

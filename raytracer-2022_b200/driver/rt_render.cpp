@@ -4,22 +4,18 @@
  *
  *   [1/5] consts -> camera            main.rs:33-78     (command line instead of editing consts)
  *   [2/5] scene + BvhNode::new_list   main.rs:89-90     rt::build_config (host/scenes.cpp), rt::lower
- *         render                      main.rs:93-163    rtgpu_render, one host thread per GPU, spp-sharded
- *   [3/5] collect                     main.rs:171-183   ONE ncclReduce(sum) of the float accumulation buffers
+ *         render                      main.rs:93-163    rtgpu_multi_render: one host thread per GPU, spp-sharded
+ *   [3/5] collect                     main.rs:171-183   ... and ONE ncclReduce(sum) of the float accumulation buffers
  *   [4/5] write_color + row flip      main.rs:191-201   rtgpu_resolve
  *   [5/5] image file                  main.rs:213-221   binary PPM (the JPEG encoder is out of scope)
  *
- * Build: see __graft_entry__.build().  Links librthost.so, librtgpu.so and the system libnccl.
+ * Build: see __graft_entry__.build().  Links librthost.so and librtgpu.so (which loads NCCL at run time).
  */
-#include <cuda_runtime.h>
-#include <nccl.h>
-
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "../host/rt_host.h"
@@ -90,76 +86,34 @@ int main(int argc, char **argv) {
     rtgpu_scene_desc desc = lowered.desc();
     const size_t n_float = (size_t)3 * a.width * a.height;
 
-    // ---- render: GPU g takes sample indices [g*spp/G, (g+1)*spp/G) of every pixel ----
-    std::vector<ncclComm_t> comms((size_t)a.devices);
-    std::vector<int> devs((size_t)a.devices);
-    for (int g = 0; g < a.devices; ++g) devs[g] = g;
-    if (a.devices > 1 && ncclCommInitAll(comms.data(), a.devices, devs.data()) != ncclSuccess) {
-        fprintf(stderr, "ncclCommInitAll failed\n");
+    // ---- render + collect: rtgpu_multi_render shards the samples over the GPUs (device g takes sample indices
+    //      [g*spp/G, (g+1)*spp/G) of every pixel) and sums the per-GPU radiance sums with one ncclReduce ----
+    std::vector<float> accum(n_float);
+    rtgpu_render_params p;
+    memset(&p, 0, sizeof p);
+    p.width = a.width;
+    p.height = a.height;
+    p.spp_begin = 0;
+    p.spp_end = a.spp;
+    p.max_depth = a.depth;
+    p.device = -1;
+    p.seed = a.seed;
+    rtgpu_stats stats;
+    double ms_reduce = 0.;
+    auto t_render = std::chrono::steady_clock::now();
+    if (rtgpu_multi_render(&desc, &p, a.devices, nullptr, accum.data(), &stats, &ms_reduce) != RTGPU_OK) {
+        fprintf(stderr, "render: %s\n", rtgpu_last_error());
         return 1;
     }
-    std::vector<float *> accum((size_t)a.devices, nullptr);
-    std::vector<rtgpu_stats> stats((size_t)a.devices);
-    std::vector<int> status((size_t)a.devices, 0);
-    auto t_render = std::chrono::steady_clock::now();
-    std::vector<std::thread> pool;
-    for (int g = 0; g < a.devices; ++g)
-        pool.emplace_back([&, g]() {
-            cudaSetDevice(g);
-            rtgpu_scene *sc = nullptr;
-            if (rtgpu_scene_create(&desc, g, &sc) != RTGPU_OK || cudaMalloc(&accum[g], n_float * sizeof(float)) != cudaSuccess) {
-                fprintf(stderr, "GPU %d: %s\n", g, rtgpu_last_error());
-                status[g] = 1;
-                return;
-            }
-            rtgpu_render_params p;
-            memset(&p, 0, sizeof p);
-            p.width = a.width;
-            p.height = a.height;
-            p.spp_begin = (int)((long long)g * a.spp / a.devices);
-            p.spp_end = (int)((long long)(g + 1) * a.spp / a.devices);
-            p.max_depth = a.depth;
-            p.device = g;
-            p.seed = a.seed;
-            p.accum_on_device = 1;
-            if (rtgpu_render(sc, &p, accum[g], &stats[g]) != RTGPU_OK) {
-                fprintf(stderr, "GPU %d: %s\n", g, rtgpu_last_error());
-                status[g] = 1;
-            }
-            rtgpu_scene_destroy(sc);
-        });
-    for (auto &t : pool) t.join();
-    for (int g = 0; g < a.devices; ++g)
-        if (status[g]) return 1;
-
-    // ---- collect: one sum-reduce of the per-GPU radiance sums to GPU 0 ----
-    printf("[3/5] Collecting results...\n");
-    if (a.devices > 1) {
-        ncclGroupStart();
-        for (int g = 0; g < a.devices; ++g) {
-            cudaSetDevice(g);
-            ncclReduce(accum[g], accum[g], n_float, ncclFloat, ncclSum, 0, comms[g], 0);
-        }
-        ncclGroupEnd();
-        for (int g = 0; g < a.devices; ++g) {
-            cudaSetDevice(g);
-            cudaStreamSynchronize(0);
-        }
-    }
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_render).count();
-    uint64_t rays = 0, samples = 0;
-    for (int g = 0; g < a.devices; ++g) {
-        rays += stats[g].rays;
-        samples += stats[g].samples;
-    }
-    printf("      %.3f s, %.1f Mrays/s, %.1f Msamples/s, %.2f rays/sample\n", sec, rays / sec / 1e6, samples / sec / 1e6,
-           (double)rays / (double)(samples ? samples : 1));
+    printf("[3/5] Collecting results... (one reduce of %.1f MB: %.2f ms)\n", n_float * 4 / 1e6, ms_reduce);
+    printf("      %.3f s, %.1f Mrays/s, %.1f Msamples/s, %.2f rays/sample\n", sec, stats.rays / sec / 1e6, stats.samples / sec / 1e6,
+           (double)stats.rays / (double)(stats.samples ? stats.samples : 1));
 
     // ---- image ----
     printf("[4/5] Generating image...\n");
     std::vector<uint8_t> rgb((size_t)3 * a.width * a.height);
-    cudaSetDevice(0);
-    if (rtgpu_resolve(accum[0], a.width, a.height, a.spp, 1, rgb.data()) != RTGPU_OK) {
+    if (rtgpu_resolve(accum.data(), a.width, a.height, a.spp, 0, rgb.data()) != RTGPU_OK) {
         fprintf(stderr, "resolve: %s\n", rtgpu_last_error());
         return 1;
     }
@@ -172,11 +126,6 @@ int main(int argc, char **argv) {
     fprintf(f, "P6\n%d %d\n255\n", a.width, a.height);
     fwrite(rgb.data(), 1, rgb.size(), f);
     fclose(f);
-    for (int g = 0; g < a.devices; ++g) {
-        cudaSetDevice(g);
-        cudaFree(accum[g]);
-        if (a.devices > 1) ncclCommDestroy(comms[g]);
-    }
     printf("\n      All Work Done.\n      Elapsed Time: %.2f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count());
     return 0;
 }

@@ -218,17 +218,21 @@ def test_per_sample_radiance(name):
     assert np.array_equal(np.isnan(g).any(axis=1), np.isnan(o).any(axis=1)) or (~finite).mean() < 0.01
 
 
-def test_one_large_wave_and_several_small_ones_give_the_same_image():
-    """bench.py renders ONE wave per step (max_paths_in_flight = all paths of the step): 1024x1024 x 20 spp = 21 M paths in one
-    wave against the same render split into waves of at most 16 Mi paths -- same rays, same image."""
+def test_pool_size_does_not_change_the_image():
+    """Path regeneration: the renderer keeps at most `max_paths_in_flight` paths alive and replaces finished paths by new
+    camera rays.  1024x1024 x 20 spp = 21 M paths through a pool that holds them all, through the default pool and through a
+    pool of 1 Mi paths (21 refills): same rays, and -- the pixel sums being exact fixed-point sums -- BIT-identical images."""
     s, orc, gpu = get("cornell_box")
     w = h = 1024
     spp = 20
     a1, st1 = gpu.render(w, h, 0, spp, seed=9, max_paths_in_flight=w * h * spp)
-    a2, st2 = gpu.render(w, h, 0, spp, seed=9, max_paths_in_flight=1 << 24)
-    assert st1.rays == st2.rays and st1.samples == st2.samples == w * h * spp
-    assert st1.launches < st2.launches  # one wave against two
-    assert np.allclose(a1, a2, rtol=1e-6, atol=1e-6)
+    a2, st2 = gpu.render(w, h, 0, spp, seed=9)
+    a3, st3 = gpu.render(w, h, 0, spp, seed=9, max_paths_in_flight=1 << 20)
+    assert st1.rays == st2.rays == st3.rays and st1.samples == st3.samples == w * h * spp
+    assert list(st1.rays_per_bounce) == list(st3.rays_per_bounce) and sum(st1.rays_per_bounce) == st1.rays
+    assert st3.launches_extend > st1.launches_extend  # more, smaller iterations
+    assert np.array_equal(a1, a2) and np.array_equal(a1, a3)
+    assert st3.pool_paths <= (1 << 20) + 256 or st3.pool_paths == st1.pool_paths  # (the pool buffer is kept between renders)
 
 
 @pytest.mark.parametrize("name", ["final_scene", "cornell_smoke", "obj_cornell"])

@@ -226,3 +226,25 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["value"] > 0 and d["steps"] == 1 and d["config"]["workload"] == "c1_random_scene_400x225"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_rust_stub_layouts_cannot_drift(tmp_path):
+    """INTEGRATION.md's unbuilt `#[repr(C)]` stub: tests/native/abi_layout.c static_asserts every size / offset / enum value
+    the stub declares against include/rtgpu.h (no Rust toolchain here, so this C translation unit stands in for rustc)."""
+    src = os.path.join(ROOT, "tests", "native", "abi_layout.c")
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-c", src, "-o", str(tmp_path / "abi_layout.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_f32_box_pretest_never_contradicts_the_f64_test(tmp_path):
+    """rt_cull.h (the f32 pre-test of AABB::hit the extend kernel runs on every BvhNode) against aabb.rs:15-32 restated in f64,
+    on 3 M random and adversarial (grazing, zero-thickness, 0*inf, running best at the entry) ray/box pairs: a CERTAIN answer of
+    the pre-test must always be the f64 answer.  (400 M pairs were run once: 0 mismatches; a 5x smaller margin fails.)"""
+    exe = str(tmp_path / "cull_fuzz")
+    src = os.path.join(ROOT, "tests", "native", "cull_fuzz.cpp")
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-o", exe, src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, "3", "2022"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "mismatches 0" in r.stdout, r.stdout + r.stderr
+    unsure = float(r.stdout.split("(")[1].split("%")[0])
+    assert unsure < 40.0  # this test set lives on the decision boundary; a render sees ~0.05 % undecided boxes

@@ -11,12 +11,13 @@ for name in names:
     spp = int(os.environ.get("KT_SPP", spp))  # KT_SPP=24: the wave size bench.py uses
     s = rt.Scene(seed=2022).build_config(name, w / h)
     gpu = rt.GpuScene(s.lower(), 0)
-    gpu.render(w, h, 0, spp)  # also sizes the wave buffers
+    pool = int(os.environ.get("KT_POOL", 0))  # paths in flight (0 = library default)
+    gpu.render(w, h, 0, spp, max_paths_in_flight=pool)  # also sizes the pool
     best = None
     for rep in range(3):
-        acc, st = gpu.render(w, h, 0, spp)
+        acc, st = gpu.render(w, h, 0, spp, max_paths_in_flight=pool)
         if best is None or st.ms_total < best.ms_total:
             best = st
     st = best
-    print(f"{name}: rays {st.rays} total {st.ms_total:.2f} ms extend {st.ms_extend:.2f} shade {st.ms_shade:.2f} other {st.ms_other:.2f} "
+    print(f"{name} [{w}x{h} x {spp} spp, pool {st.pool_paths} paths / {st.pool_bytes / 1e9:.2f} GB, {st.launches_extend} iterations]: rays {st.rays} total {st.ms_total:.2f} ms extend {st.ms_extend:.2f} shade {st.ms_shade:.2f} other {st.ms_other:.2f} "
           f"-> {st.rays / st.ms_total / 1e3:.1f} Mrays/s (extend-only {st.rays / st.ms_extend / 1e3:.1f}, shade-only {st.rays / st.ms_shade / 1e3:.1f})")
