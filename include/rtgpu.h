@@ -108,15 +108,19 @@ typedef struct rtgpu_perlin {
     int32_t perm_x[256], perm_y[256], perm_z[256];
 } rtgpu_perlin;
 
-/* members of the `lights` HittableList (main.rs:89): only Sphere and the three rects
- * implement pdf_value/random; anything else keeps the trait defaults (pdf 0, direction
- * (1,0,0), hittable/mod.rs:62-67) and is lowered as DEAD */
+/* members of the `lights` HittableList (main.rs:89).  Sphere and the three rects implement pdf_value/random
+ * (sphere.rs:75-90, aarect.rs:74-93,157-176,240-259) and so does a HittableList nested in `lights`
+ * (hittable/mod.rs:121-132: mean of its members' pdf_value, uniform pick for random) -- LIST, whose members are the
+ * entries [first, first + count) of the same array.  Anything else keeps the trait defaults (pdf 0, direction
+ * (1,0,0), hittable/mod.rs:62-67) and is lowered as DEAD.  The members of `lights` itself are the first
+ * n_light_roots entries. */
 enum rtgpu_light_kind { RTGPU_LIGHT_RECT_XY = 0, RTGPU_LIGHT_RECT_XZ = 1, RTGPU_LIGHT_RECT_YZ = 2,
-                        RTGPU_LIGHT_SPHERE = 3, RTGPU_LIGHT_DEAD = 4 };
+                        RTGPU_LIGHT_SPHERE = 3, RTGPU_LIGHT_DEAD = 4, RTGPU_LIGHT_LIST = 5 };
+#define RTGPU_MAX_LIGHT_NESTING 4 /* lists inside lists inside `lights` */
 typedef struct rtgpu_light {
     uint32_t kind;
     uint32_t gid;
-    double p[5]; /* rect: a0 a1 b0 b1 k;  sphere: center(3) radius */
+    double p[5]; /* rect: a0 a1 b0 b1 k;  sphere: center(3) radius;  LIST: first, count (exact small integers) */
 } rtgpu_light;
 
 typedef struct rtgpu_camera { /* basic/camera.rs:9-20 */
@@ -138,7 +142,9 @@ typedef struct rtgpu_scene_desc {
     const rtgpu_light *lights;
     uint32_t n_ops, n_xforms, n_chain, n_ctxs;
     uint32_t n_materials, n_textures, n_perlins, n_images, n_lights;
-    uint32_t max_push_depth; /* deepest PUSH nesting in the program */
+    uint32_t max_push_depth; /* deepest PUSH nesting in the program (informative: rtgpu_scene_create counts it itself) */
+    uint32_t n_light_roots;  /* members of `lights` itself = lights[0 .. n_light_roots); the rest are members of nested lists */
+    uint32_t pad_;
     uint64_t n_texel_bytes;
     rtgpu_camera camera;
     double background[3]; /* main.rs:51 */

@@ -1524,17 +1524,39 @@ extern "C" {
 
 int64_t orc_dump_rays(const orc_scene *s, int w, int h, int spp, int max_depth, uint64_t seed, int bounce,
                       int64_t cap, orc_ray *out) {
-    RayDump d{bounce, cap, 0, out};
-    for (int y = 0; y < h && d.n < cap; ++y)
-        for (int x = 0; x < w && d.n < cap; ++x)
-            for (int i = 0; i < spp && d.n < cap; ++i) {
-                Rng rng(seed, (uint32_t)(y * w + x), (uint32_t)i, DOMAIN_PATH);
-                tl_rng = &rng;
-                Ray r = camera_sample(*s, w, h, x, y);
-                ray_color_dump(r, *s, max_depth, 0, d);
-            }
-    tl_rng = nullptr;
-    return d.n;
+    /* The first `cap` rays of the given bounce in (y, x, sample) order.  Rows are traced by all host threads, a band of rows
+     * per round, each row into its own buffer; the buffers are appended in row order, so the result does not depend on
+     * the number of threads (tests dump 2^20 rays per scene and bounce). */
+    unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+    int64_t n = 0;
+    for (int y0 = 0; y0 < h && n < cap; y0 += (int)nt) {
+        int rows = std::min<int>((int)nt, h - y0);
+        std::vector<std::vector<orc_ray>> buf((size_t)rows);
+        std::vector<std::thread> pool;
+        for (int k = 0; k < rows; ++k)
+            pool.emplace_back([&, k]() {
+                int y = y0 + k;
+                int64_t room = cap - n; /* no row needs more than what is still missing */
+                buf[k].resize((size_t)std::min<int64_t>(room, (int64_t)w * spp));
+                RayDump d{bounce, (int64_t)buf[k].size(), 0, buf[k].data()};
+                for (int x = 0; x < w && d.n < d.cap; ++x)
+                    for (int i = 0; i < spp && d.n < d.cap; ++i) {
+                        Rng rng(seed, (uint32_t)(y * w + x), (uint32_t)i, DOMAIN_PATH);
+                        tl_rng = &rng;
+                        Ray r = camera_sample(*s, w, h, x, y);
+                        ray_color_dump(r, *s, max_depth, 0, d);
+                    }
+                tl_rng = nullptr;
+                buf[k].resize((size_t)d.n);
+            });
+        for (auto &th : pool) th.join();
+        for (int k = 0; k < rows && n < cap; ++k) {
+            int64_t take = std::min<int64_t>((int64_t)buf[k].size(), cap - n);
+            std::memcpy(out + n, buf[k].data(), (size_t)take * sizeof(orc_ray));
+            n += take;
+        }
+    }
+    return n;
 }
 
 void orc_write_color(const double rgb_sum[3], int spp, uint8_t out[3]) { // main.rs:280-299

@@ -110,7 +110,7 @@ class rtgpu_scene_desc(C.Structure):
         ("n_ops", C.c_uint32), ("n_xforms", C.c_uint32), ("n_chain", C.c_uint32), ("n_ctxs", C.c_uint32),
         ("n_materials", C.c_uint32), ("n_textures", C.c_uint32), ("n_perlins", C.c_uint32), ("n_images", C.c_uint32),
         ("n_lights", C.c_uint32),
-        ("max_push_depth", C.c_uint32),
+        ("max_push_depth", C.c_uint32), ("n_light_roots", C.c_uint32), ("pad_", C.c_uint32),
         ("n_texel_bytes", C.c_uint64),
         ("camera", rtgpu_camera),
         ("background", c_double3),

@@ -68,7 +68,7 @@ struct DScene {
     const rtgpu_image *images;
     const uint8_t *texels;
     const rtgpu_light *lights;
-    uint32_t n_units, n_lights;
+    uint32_t n_units, n_lights, n_light_roots;
     float extent; /* largest |coordinate| of any BvhNode box (>= RT_CULL_MIN_EXTENT): the B of rt_cull.h */
     rtgpu_camera cam;
     double background[3];
@@ -985,34 +985,64 @@ __device__ __forceinline__ double rect_pdf_value(const rtgpu_light &l, V3 o, V3 
     double cosv = fabs(dot(v, n) / length(v));
     return dis_sqr / (cosv * area);
 }
-__device__ __noinline__ double lights_pdf_value(const DScene &sc, V3 o, V3 v) {
-    double sum = 0.;
-    for (uint32_t i = 0; i < sc.n_lights; ++i) {
-        const rtgpu_light &l = sc.lights[i];
-        double pv = 0.;
-        switch (l.kind) {
-        case RTGPU_LIGHT_RECT_XY: pv = rect_pdf_value<2>(l, o, v); break;
-        case RTGPU_LIGHT_RECT_XZ: pv = rect_pdf_value<1>(l, o, v); break;
-        case RTGPU_LIGHT_RECT_YZ: pv = rect_pdf_value<0>(l, o, v); break;
-        case RTGPU_LIGHT_SPHERE: { /* sphere.rs:75-83 */
-            V3 c = v3(l.p[0], l.p[1], l.p[2]);
-            double best = CUDART_INF;
-            if (hit_sphere(o, v, length_sqr(v), c, l.p[3], 0.001, best)) {
-                double cos_max = sqrt(1. - l.p[3] * l.p[3] / length_sqr(c - o));
-                double solid_angle = 2. * RT_PI * (1. - cos_max);
-                pv = 1. / solid_angle;
-            }
-            break;
+/* pdf_value of one member that is not a list */
+__device__ __forceinline__ double light_pdf_value(const rtgpu_light &l, V3 o, V3 v) {
+    switch (l.kind) {
+    case RTGPU_LIGHT_RECT_XY: return rect_pdf_value<2>(l, o, v);
+    case RTGPU_LIGHT_RECT_XZ: return rect_pdf_value<1>(l, o, v);
+    case RTGPU_LIGHT_RECT_YZ: return rect_pdf_value<0>(l, o, v);
+    case RTGPU_LIGHT_SPHERE: { /* sphere.rs:75-83 */
+        V3 c = v3(l.p[0], l.p[1], l.p[2]);
+        double best = CUDART_INF;
+        if (hit_sphere(o, v, length_sqr(v), c, l.p[3], 0.001, best)) {
+            double cos_max = sqrt(1. - l.p[3] * l.p[3] / length_sqr(c - o));
+            double solid_angle = 2. * RT_PI * (1. - cos_max);
+            return 1. / solid_angle;
         }
-        default: pv = 0.; break; /* trait default, hittable/mod.rs:62-64 */
-        }
-        sum += pv;
+        return 0.;
     }
-    return sum / (double)sc.n_lights;
+    default: return 0.; /* trait default, hittable/mod.rs:62-64 */
+    }
 }
+/* HittableList::pdf_value (hittable/mod.rs:121-128) over `lights`: the mean of the members' values, a member that is a
+ * HittableList contributing the mean over ITS members.  Sums run in member order, as upstream; the recursion is unrolled
+ * over an explicit stack (RTGPU_MAX_LIGHT_NESTING levels, checked when the scene is created). */
+__device__ __noinline__ double lights_pdf_value(const DScene &sc, V3 o, V3 v) {
+    uint32_t at[RTGPU_MAX_LIGHT_NESTING + 1], end[RTGPU_MAX_LIGHT_NESTING + 1];
+    double sum[RTGPU_MAX_LIGHT_NESTING + 1], len[RTGPU_MAX_LIGHT_NESTING + 1];
+    int sp = 0;
+    at[0] = 0;
+    end[0] = sc.n_light_roots;
+    sum[0] = 0.;
+    len[0] = (double)sc.n_light_roots;
+    for (;;) {
+        if (at[sp] < end[sp]) {
+            const rtgpu_light &l = sc.lights[at[sp]++];
+            if (l.kind == RTGPU_LIGHT_LIST && sp < RTGPU_MAX_LIGHT_NESTING) {
+                ++sp;
+                at[sp] = (uint32_t)l.p[0];
+                end[sp] = at[sp] + (uint32_t)l.p[1];
+                sum[sp] = 0.;
+                len[sp] = l.p[1];
+            } else {
+                sum[sp] += light_pdf_value(l, o, v);
+            }
+        } else {
+            double val = sum[sp] / len[sp];
+            if (sp == 0) return val;
+            --sp;
+            sum[sp] += val;
+        }
+    }
+}
+/* HittableList::random (hittable/mod.rs:129-132): uniform pick of a member (one draw), then that member's random();
+ * a member that is a HittableList picks again */
 __device__ __noinline__ V3 lights_random(const DScene &sc, V3 o, rt_rng &rng) {
-    uint32_t target = rng.gen_index(sc.n_lights);
-    const rtgpu_light &l = sc.lights[target];
+    uint32_t target = rng.gen_index(sc.n_light_roots);
+    const rtgpu_light *lp = sc.lights + target;
+    for (int depth = 0; lp->kind == RTGPU_LIGHT_LIST && depth < RTGPU_MAX_LIGHT_NESTING; ++depth)
+        lp = sc.lights + (uint32_t)lp->p[0] + rng.gen_index((uint32_t)lp->p[1]);
+    const rtgpu_light &l = *lp;
     switch (l.kind) {
     case RTGPU_LIGHT_RECT_XY: { /* aarect.rs:85-93 */
         double a = rng.gen_range(l.p[0], l.p[1]);

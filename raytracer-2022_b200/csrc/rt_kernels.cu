@@ -483,7 +483,7 @@ __device__ __forceinline__ bool shade_segment(const DScene &sc, const Ray &r, do
             Onb uvw = onb_from_w(rec.n); /* CosPdf::new(rec.normal), pdf.rs:35-39 */
             V3 direction;
             double pdf_val;
-            if (sc.n_lights == 0) {
+            if (sc.n_light_roots == 0) {
                 /* Q12: empty `lights` -> the cosine pdf alone (decision shared with the oracle) */
                 direction = onb_local(uvw, random_cosine_direction(rng));
                 double c = dot(to_unit(direction), uvw.w);
@@ -894,12 +894,26 @@ rtgpu_status validate(const rtgpu_scene_desc *d) {
             (uint64_t)im.offset + (uint64_t)im.width * (uint64_t)im.height * 3 > d->n_texel_bytes)
             return bad("image outside the texel buffer");
     }
-    for (uint32_t i = 0; i < d->n_lights; ++i) {
-        const rtgpu_light &l = d->lights[i];
-        if (l.kind > RTGPU_LIGHT_DEAD) return bad("unknown light kind");
-        int np = l.kind == RTGPU_LIGHT_SPHERE ? 4 : (l.kind == RTGPU_LIGHT_DEAD ? 0 : 5);
-        for (int k = 0; k < np; ++k)
-            if (!(l.p[k] == l.p[k])) return bad("NaN light parameter");
+    if (d->n_light_roots > d->n_lights || (d->n_lights > 0 && d->n_light_roots == 0)) return bad("n_light_roots out of range");
+    {
+        /* nesting depth of every entry: roots are level 0; the members of a LIST lie behind it and one level deeper */
+        std::vector<uint8_t> level(d->n_lights, 0);
+        for (uint32_t i = 0; i < d->n_lights; ++i) {
+            const rtgpu_light &l = d->lights[i];
+            if (l.kind > RTGPU_LIGHT_LIST) return bad("unknown light kind");
+            if (l.kind == RTGPU_LIGHT_LIST) {
+                if (!(l.p[0] >= 0. && l.p[1] >= 1. && l.p[0] <= 1048576. && l.p[1] <= 1048576.)) return bad("bad light list range");
+                uint32_t first = (uint32_t)l.p[0], count = (uint32_t)l.p[1];
+                if ((double)first != l.p[0] || (double)count != l.p[1]) return bad("bad light list range");
+                if (first <= i || first < d->n_light_roots || (uint64_t)first + count > d->n_lights) return bad("light list members out of range");
+                if (level[i] + 1 > RTGPU_MAX_LIGHT_NESTING) return bad("light lists nested deeper than RTGPU_MAX_LIGHT_NESTING");
+                for (uint32_t k = first; k < first + count; ++k) level[k] = (uint8_t)(level[i] + 1);
+                continue;
+            }
+            int np = l.kind == RTGPU_LIGHT_SPHERE ? 4 : (l.kind == RTGPU_LIGHT_DEAD ? 0 : 5);
+            for (int k = 0; k < np; ++k)
+                if (!(l.p[k] == l.p[k])) return bad("NaN light parameter");
+        }
     }
     return RTGPU_OK;
 }
@@ -1305,6 +1319,7 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
     s->d.n_units = n_units;
     s->d.extent = extent;
     s->d.n_lights = desc->n_lights;
+    s->d.n_light_roots = desc->n_light_roots;
     s->d.cam = desc->camera;
     for (int c = 0; c < 3; ++c) s->d.background[c] = desc->background[c];
     *out = s;

@@ -260,6 +260,7 @@ rtgpu_scene_desc Lowered::desc() const {
     d.n_perlins = (uint32_t)perlins.size();
     d.n_images = (uint32_t)images.size();
     d.n_lights = (uint32_t)lights.size();
+    d.n_light_roots = n_light_roots;
     d.max_push_depth = max_push_depth;
     d.n_texel_bytes = texels.size();
     d.camera = camera;
@@ -320,23 +321,47 @@ Lowered lower(const rt_graph &g, bool elide_singletons) {
         out.images.push_back(im);
     }
     out.texels.assign(g.texels, g.texels + g.n_texel_bytes);
-    for (int i = 0; i < g.n_lights; ++i) {
-        int32_t id = g.lights[i];
-        if (id < 0 || id >= g.n_objects) throw Error{"lower: light id out of range"};
-        const rt_object &o = g.objects[id];
-        rtgpu_light l;
-        std::memset(&l, 0, sizeof l);
-        l.gid = (uint32_t)id;
-        switch (o.kind) {
-        case RT_OBJ_XY_RECT: l.kind = RTGPU_LIGHT_RECT_XY; break;
-        case RT_OBJ_XZ_RECT: l.kind = RTGPU_LIGHT_RECT_XZ; break;
-        case RT_OBJ_YZ_RECT: l.kind = RTGPU_LIGHT_RECT_YZ; break;
-        case RT_OBJ_SPHERE: l.kind = RTGPU_LIGHT_SPHERE; break;
-        default: l.kind = RTGPU_LIGHT_DEAD; break; // trait defaults, hittable/mod.rs:62-67
+    /* `lights` (main.rs:89) is a HittableList: its members become lights[0 .. n_light_roots); a member that is itself a
+     * HittableList is live upstream (hittable/mod.rs:121-132) and becomes a LIST entry whose members follow, level by level */
+    {
+        struct Pending { size_t entry; int32_t list_obj; int depth; };
+        std::vector<Pending> todo;
+        auto lower_member = [&](int32_t id, int depth) {
+            if (id < 0 || id >= g.n_objects) throw Error{"lower: light id out of range"};
+            const rt_object &o = g.objects[id];
+            rtgpu_light l;
+            std::memset(&l, 0, sizeof l);
+            l.gid = (uint32_t)id;
+            switch (o.kind) {
+            case RT_OBJ_XY_RECT: l.kind = RTGPU_LIGHT_RECT_XY; break;
+            case RT_OBJ_XZ_RECT: l.kind = RTGPU_LIGHT_RECT_XZ; break;
+            case RT_OBJ_YZ_RECT: l.kind = RTGPU_LIGHT_RECT_YZ; break;
+            case RT_OBJ_SPHERE: l.kind = RTGPU_LIGHT_SPHERE; break;
+            case RT_OBJ_LIST: l.kind = RTGPU_LIGHT_LIST; break;
+            default: l.kind = RTGPU_LIGHT_DEAD; break; // trait defaults, hittable/mod.rs:62-67 (wrappers do not forward either)
+            }
+            if (l.kind == RTGPU_LIGHT_LIST) {
+                if (depth >= RTGPU_MAX_LIGHT_NESTING) throw Error{"lower: HittableLists nested deeper than RTGPU_MAX_LIGHT_NESTING inside `lights`"};
+                if (o.c0 < 0 || o.c1 < 0 || o.c0 + o.c1 > g.n_list_items) throw Error{"lower: bad list range"};
+                // HittableList::random picks with gen_range(0..len): an empty list panics upstream (hittable/mod.rs:130)
+                if (o.c1 == 0) throw Error{"lower: an empty HittableList inside `lights` panics upstream (gen_range on an empty range)"};
+                todo.push_back(Pending{out.lights.size(), id, depth});
+            } else {
+                int np = l.kind == RTGPU_LIGHT_SPHERE ? 4 : (l.kind == RTGPU_LIGHT_DEAD ? 0 : 5);
+                for (int k = 0; k < np; ++k) l.p[k] = o.p[k];
+            }
+            out.lights.push_back(l);
+        };
+        for (int i = 0; i < g.n_lights; ++i) lower_member(g.lights[i], 0);
+        out.n_light_roots = (uint32_t)out.lights.size();
+        for (size_t k = 0; k < todo.size(); ++k) { // (todo grows while nested lists are found)
+            Pending pd = todo[k];
+            const rt_object &lo = g.objects[pd.list_obj];
+            out.lights[pd.entry].p[0] = (double)out.lights.size();
+            out.lights[pd.entry].p[1] = (double)lo.c1;
+            for (int m = 0; m < lo.c1; ++m) lower_member(g.list_items[lo.c0 + m], pd.depth + 1);
+            if (out.lights.size() > (1u << 20)) throw Error{"lower: too many lights"};
         }
-        int np = l.kind == RTGPU_LIGHT_SPHERE ? 4 : (l.kind == RTGPU_LIGHT_DEAD ? 0 : 5);
-        for (int k = 0; k < np; ++k) l.p[k] = o.p[k];
-        out.lights.push_back(l);
     }
     const rt_camera &c = g.camera;
     for (int k = 0; k < 3; ++k) {

@@ -202,6 +202,7 @@ struct Lowered {
     std::vector<rtgpu_image> images;
     std::vector<uint8_t> texels;
     std::vector<rtgpu_light> lights;
+    uint32_t n_light_roots = 0; /* members of `lights` itself; members of nested lists follow */
     uint32_t max_push_depth = 0;
     rtgpu_camera camera;
     double background[3];

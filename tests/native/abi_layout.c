@@ -35,15 +35,16 @@ SIZE(rtgpu_camera, 168); OFF(rtgpu_camera, origin, 0); OFF(rtgpu_camera, lower_l
 OFF(rtgpu_camera, vertical, 72); OFF(rtgpu_camera, u, 96); OFF(rtgpu_camera, v, 120); OFF(rtgpu_camera, lens_radius, 144);
 OFF(rtgpu_camera, time0, 152); OFF(rtgpu_camera, time1, 160);
 /* RtgpuSceneDesc { ops, xforms, chain, ctxs, materials, textures, perlins, images, texels, lights: *const _ (10 pointers),
- *                  n_ops, n_xforms, n_chain, n_ctxs, n_materials, n_textures, n_perlins, n_images, n_lights, max_push_depth: u32,
- *                  n_texel_bytes: u64, camera: RtgpuCamera, background: [f64; 3] } */
-SIZE(rtgpu_scene_desc, 80 + 40 + 8 + 168 + 24); OFF(rtgpu_scene_desc, ops, 0); OFF(rtgpu_scene_desc, xforms, 8); OFF(rtgpu_scene_desc, chain, 16);
+ *                  n_ops, n_xforms, n_chain, n_ctxs, n_materials, n_textures, n_perlins, n_images, n_lights, max_push_depth,
+ *                  n_light_roots, pad: u32 (12 of them), n_texel_bytes: u64, camera: RtgpuCamera, background: [f64; 3] } */
+SIZE(rtgpu_scene_desc, 80 + 48 + 8 + 168 + 24); OFF(rtgpu_scene_desc, ops, 0); OFF(rtgpu_scene_desc, xforms, 8); OFF(rtgpu_scene_desc, chain, 16);
 OFF(rtgpu_scene_desc, ctxs, 24); OFF(rtgpu_scene_desc, materials, 32); OFF(rtgpu_scene_desc, textures, 40); OFF(rtgpu_scene_desc, perlins, 48);
 OFF(rtgpu_scene_desc, images, 56); OFF(rtgpu_scene_desc, texels, 64); OFF(rtgpu_scene_desc, lights, 72); OFF(rtgpu_scene_desc, n_ops, 80);
 OFF(rtgpu_scene_desc, n_xforms, 84); OFF(rtgpu_scene_desc, n_chain, 88); OFF(rtgpu_scene_desc, n_ctxs, 92); OFF(rtgpu_scene_desc, n_materials, 96);
 OFF(rtgpu_scene_desc, n_textures, 100); OFF(rtgpu_scene_desc, n_perlins, 104); OFF(rtgpu_scene_desc, n_images, 108);
-OFF(rtgpu_scene_desc, n_lights, 112); OFF(rtgpu_scene_desc, max_push_depth, 116); OFF(rtgpu_scene_desc, n_texel_bytes, 120);
-OFF(rtgpu_scene_desc, camera, 128); OFF(rtgpu_scene_desc, background, 296);
+OFF(rtgpu_scene_desc, n_lights, 112); OFF(rtgpu_scene_desc, max_push_depth, 116); OFF(rtgpu_scene_desc, n_light_roots, 120);
+OFF(rtgpu_scene_desc, pad_, 124); OFF(rtgpu_scene_desc, n_texel_bytes, 128); OFF(rtgpu_scene_desc, camera, 136);
+OFF(rtgpu_scene_desc, background, 304);
 /* RtgpuRay { o: [f64; 3], d: [f64; 3], tm: f64, t_min: f64, t_max: f64 } */
 SIZE(rtgpu_ray, 72); OFF(rtgpu_ray, o, 0); OFF(rtgpu_ray, d, 24); OFF(rtgpu_ray, tm, 48); OFF(rtgpu_ray, t_min, 56); OFF(rtgpu_ray, t_max, 64);
 /* RtgpuHit { t: f64, p: [f64; 3], n: [f64; 3], u: f64, v: f64, hit: i32, front_face: i32, gid: i32, face: i32, inst: i32, mat: i32,
@@ -70,4 +71,5 @@ _Static_assert(RTGPU_OP_NODE == 0 && RTGPU_OP_SPHERE == 1 && RTGPU_OP_MSPHERE ==
                    RTGPU_OP_RECT_YZ == 5 && RTGPU_OP_BOX == 6 && RTGPU_OP_TRI == 7 && RTGPU_OP_MEDIUM == 8 && RTGPU_OP_PUSH == 9 &&
                    RTGPU_OP_POP == 10 && RTGPU_OP_RING == 11, "op kinds");
 _Static_assert(RTGPU_XF_TRANSLATE == 0 && RTGPU_XF_ROTATE_Y == 1 && RTGPU_XF_ZOOM == 2 && RTGPU_XF_FLIP == 3, "xform kinds");
-_Static_assert(RTGPU_LIGHT_RECT_XY == 0 && RTGPU_LIGHT_RECT_XZ == 1 && RTGPU_LIGHT_RECT_YZ == 2 && RTGPU_LIGHT_SPHERE == 3, "light kinds");
+_Static_assert(RTGPU_LIGHT_RECT_XY == 0 && RTGPU_LIGHT_RECT_XZ == 1 && RTGPU_LIGHT_RECT_YZ == 2 && RTGPU_LIGHT_SPHERE == 3 && RTGPU_LIGHT_DEAD == 4 &&
+                   RTGPU_LIGHT_LIST == 5, "light kinds");

@@ -199,8 +199,9 @@ def test_constant_medium_draws_match():
 @pytest.mark.parametrize("name", ["cornell_box", "random_scene", "final_scene", "cornell_book3", "cornell_smoke", "obj_cornell", "wwscene"])
 def test_per_sample_radiance(name):
     """Same Philox slots, same control flow: one-sample radiance agrees path by path.  Paths
-    whose direction passes through GPU sin/cos/acos (1-ulp differences) can diverge after many
-    bounces on curved surfaces, so a small fraction of outliers is allowed and counted."""
+    whose direction passes through GPU sin/cos/acos/log (1-ulp differences) could diverge after many
+    bounces on curved surfaces; on the B200 none of these 4096 paths per scene does (profiles/parity_r02.json:
+    1.0 / 1.0 on all seven scenes), the bound leaves room for 0.5 %."""
     s, orc, gpu = get(name)
     w = h = 64
     n = w * h
@@ -214,7 +215,7 @@ def test_per_sample_radiance(name):
     frac = (close | ~finite).mean()
     same_len = (grays == orays).mean()
     print(f"{name}: {frac:.4f} of paths equal, {same_len:.4f} same length, rays gpu {grays.sum()} oracle {orays.sum()}")
-    assert frac >= 0.97 and same_len >= 0.97
+    assert frac >= 0.995 and same_len >= 0.995
     assert np.array_equal(np.isnan(g).any(axis=1), np.isnan(o).any(axis=1)) or (~finite).mean() < 0.01
 
 

@@ -3,6 +3,7 @@ asset loaders, and that the C-ABI library loads and exports every symbol of incl
 import ctypes as C
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
