@@ -28,6 +28,8 @@
 #endif
 #define RT_MAX_PUSH 4   /* nesting of PUSH ops (instances inside instances) */
 #define RT_MAX_CHAIN 8  /* wrappers around one primitive */
+#define RT_CLASS_ISOTROPIC 5u  /* shade classes: see k_classify in rt_kernels.cu */
+#define RT_KIND_UNSURE_NODE 12u /* in registers only: a fetched NODE whose box the f32 pre-test could not decide */
 #define RT_PI 3.14159265358979323846264338327950288
 #define RT_F64_MAX 1.7976931348623157e308
 
@@ -232,6 +234,7 @@ struct Closest {
     double t;      /* running best (= t_max when nothing was hit) */
     uint32_t op;   /* unit index of the winning op, RT_NO_HIT if none */
     uint32_t face; /* box side of the winner */
+    uint32_t cls;  /* shade class of the winner's material: word 1 of a leaf op's header on the device (rt_kernels.cu, repack_program) */
 };
 
 /* Walks units [begin, end) in order -- the reference's left-then-right recursion unrolled
@@ -268,8 +271,8 @@ __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_
 /* phases of the warp scheduler: ops whose code is the same run together */
 enum { PH_NODE = 0, PH_SPHERE = 1, PH_BOX = 2, PH_TRI = 3, PH_MISC = 4, PH_EXACT = 5, PH_NONE = 7 };
 __device__ __forceinline__ uint32_t phase_of_kind(uint32_t kind) {
-    /* NODE SPHERE MSPHERE RECT_XY RECT_XZ RECT_YZ BOX TRI MEDIUM PUSH POP RING, 3 bits each */
-    return (uint32_t)((0444432444110ull >> (3 * kind)) & 7ull);
+    /* NODE SPHERE MSPHERE RECT_XY RECT_XZ RECT_YZ BOX TRI MEDIUM PUSH POP RING UNSURE_NODE, 3 bits each */
+    return (uint32_t)((05444432444110ull >> (3 * kind)) & 7ull);
 }
 
 struct SavedRays {
@@ -292,7 +295,6 @@ struct Traversal {
     Closest best;
     uint32_t i, end;
     int sp;
-    bool unsure; /* the NODE at unit i could not be decided in f32: it waits for exec_node_exact */
     uint4 h;     /* bytes 0..15 of unit i: header of a leaf op / kind|ordinal, skip, box min.xy of a NODE */
     double p[6]; /* bytes 16..63: payload of a leaf op / rest of the NODE box, then unit i+1 */
     /* the PUSH/POP stack lives OUTSIDE this struct (SavedRays): it is indexed dynamically, and an
@@ -333,6 +335,7 @@ struct Traversal {
         best.t = tmax;
         best.op = RT_NO_HIT;
         best.face = 0;
+        best.cls = 0;
         ray.set_od(o, d);
         ray.set_times(tm_, tmin_);
         derive(o, d, tmin_, sc.extent);
@@ -340,11 +343,11 @@ struct Traversal {
         i = begin;
         end = end_;
         sp = 0;
-        unsure = false;
         fetch_op(sc);
     }
     __device__ __forceinline__ bool done() const { return i >= end; }
-    __device__ __forceinline__ uint32_t phase() const { return unsure ? (uint32_t)PH_EXACT : phase_of_kind(h.x & 0xffu); }
+    __device__ __forceinline__ uint32_t phase() const { return phase_of_kind(h.x & 0xffu); }
+    __device__ __forceinline__ bool at_node() const { return (h.x & 0xffu) == RTGPU_OP_NODE; } /* = phase() == PH_NODE, two instructions */
 
     /* BvhNode::hit's box test (bvh/mod.rs:87) for the NODE at unit i and -- same fetch -- for the NODE that
      * follows it, if any: that is its left child, tested next anyway when the first box is hit.  Both answers
@@ -356,7 +359,7 @@ struct Traversal {
         uint32_t bw = (uint32_t)__double2loint(p[2]), bskip = (uint32_t)__double2hiint(p[2]);
         int rb = cull_box(c, lo_f32(p[3]), hi_f32(p[3]), lo_f32(p[4]), hi_f32(p[4]), lo_f32(p[5]), hi_f32(p[5]), bestL, bestU);
         if (ra == RT_CULL_UNSURE) {
-            unsure = true;
+            h.x |= RT_KIND_UNSURE_NODE; /* (kind NODE is 0) the fetched unit now reads as "a NODE that needs the f64 test": phase PH_EXACT */
             return;
         }
         uint32_t nxt = i + 1; /* first box hit; what follows is a leaf, or a NODE the pre-test could not decide */
@@ -377,7 +380,6 @@ struct Traversal {
         RaySigns sg;
         sg.m = (inv.x < 0. ? 1u : 0u) | (inv.y < 0. ? 2u : 0u) | (inv.z < 0. ? 4u : 0u);
         i = hit_aabb(ray.o(), inv, sg, b, ray.tmin(), best.t) ? i + 1 : h.y;
-        unsure = false;
         fetch_op(sc);
     }
     __device__ __forceinline__ void exec_sphere(const TravScene sc) {
@@ -392,6 +394,7 @@ struct Traversal {
         V3 d = ray.d();
         if (hit_sphere(ray.o(), d, length_sqr(d), c0, p[3], ray.tmin(), best.t)) {
             best.op = i;
+            best.cls = h.y;
             set_best_bounds();
         }
         i += width;
@@ -400,6 +403,7 @@ struct Traversal {
     __device__ __forceinline__ void exec_box(const TravScene sc) {
         if (hit_box(ray.o(), ray.d(), p, ray.tmin(), best.t, best.face)) {
             best.op = i;
+            best.cls = h.y;
             set_best_bounds();
         }
         i += 2;
@@ -411,6 +415,7 @@ struct Traversal {
         if (hit_triangle(ray.o(), ray.d(), v3(p[0], p[1], p[2]), v3(p[3], p[4], p[5]), v3(q[0], q[1], q[2]), v3(q[3], q[4], q[5]),
                          ray.tmin(), best.t)) {
             best.op = i;
+            best.cls = h.y;
             set_best_bounds();
         }
         i += 4;
@@ -436,22 +441,22 @@ struct Traversal {
         switch (kind) {
         case RTGPU_OP_RECT_XY:
             hit = hit_rect<2>(o, d, p[0], p[1], p[2], p[3], p[4], tmin, best.t);
-            if (hit) best.op = i;
+            if (hit) { best.op = i; best.cls = h.y; }
             i += 2;
             break;
         case RTGPU_OP_RECT_XZ:
             hit = hit_rect<1>(o, d, p[0], p[1], p[2], p[3], p[4], tmin, best.t);
-            if (hit) best.op = i;
+            if (hit) { best.op = i; best.cls = h.y; }
             i += 2;
             break;
         case RTGPU_OP_RECT_YZ:
             hit = hit_rect<0>(o, d, p[0], p[1], p[2], p[3], p[4], tmin, best.t);
-            if (hit) best.op = i;
+            if (hit) { best.op = i; best.cls = h.y; }
             i += 2;
             break;
         case RTGPU_OP_RING:
             hit = hit_ring(o, d, p[0], p[1], tmin, best.t);
-            if (hit) best.op = i;
+            if (hit) { best.op = i; best.cls = h.y; }
             i += 2;
             break;
         case RTGPU_OP_MEDIUM:
@@ -490,6 +495,7 @@ struct Traversal {
                         if (!(hit_distance > distance_inside_boundary)) {
                             best.t = t1 + hit_distance / ray_length;
                             best.op = i;
+                            best.cls = RT_CLASS_ISOTROPIC; /* a ConstantMedium scatters with its Isotropic material (constantmedium.rs:77) */
                             hit = true;
                         }
                     }
@@ -616,20 +622,20 @@ __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_
         bool node_ran = false;
 #pragma unroll 1
         for (;;) {
-            bool in_node = active && tr.phase() == PH_NODE;
+            bool in_node = active && tr.at_node();
             uint32_t m = __ballot_sync(0xffffffffu, in_node);
             if ((uint32_t)__popc(m) < node_quorum) break;
             node_ran = true;
             if (in_node) {
                 tr.exec_node(ts);
 #if RT_NODE_UNROLL >= 2
-                if (!tr.done() && tr.phase() == PH_NODE) tr.exec_node(ts); /* second box under the same vote */
+                if (!tr.done() && tr.at_node()) tr.exec_node(ts); /* second box under the same vote */
 #endif
 #if RT_NODE_UNROLL >= 3
-                if (!tr.done() && tr.phase() == PH_NODE) tr.exec_node(ts);
+                if (!tr.done() && tr.at_node()) tr.exec_node(ts);
 #endif
 #if RT_NODE_UNROLL >= 4
-                if (!tr.done() && tr.phase() == PH_NODE) tr.exec_node(ts);
+                if (!tr.done() && tr.at_node()) tr.exec_node(ts);
 #endif
                 if (tr.done()) {
                     io.store(cur, tr.best, rng_pos);
@@ -643,7 +649,7 @@ __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_
         bool hold = false;
 #if RT_MEDIUM_QUORUM > 1
         {
-            bool at_medium = active && !tr.unsure && (tr.h.x & 0xffu) == RTGPU_OP_MEDIUM;
+            bool at_medium = active && (tr.h.x & 0xffu) == RTGPU_OP_MEDIUM;
             uint32_t mm = __ballot_sync(0xffffffffu, at_medium);
             if (mm) {
                 /* hold only while something else certainly advances this iteration (a NODE round ran, or another

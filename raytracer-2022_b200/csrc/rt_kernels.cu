@@ -138,7 +138,7 @@ __device__ __forceinline__ void st_beta(StateRec *p, V3 b) {
 struct __align__(16) HitRec16 {
     double t;
     uint32_t op;  /* unit index | box face << 29; RT_NO_HIT = miss */
-    uint32_t rng; /* the path's Philox slot after the walk (ConstantMedium draws) */
+    uint32_t rng; /* the path's Philox slot after the walk (ConstantMedium draws), low 20 bits | shade class << 29 */
 };
 struct HitBuf {
     HitRec16 *rec;
@@ -262,7 +262,7 @@ struct QueueIO {
         v.x = (uint32_t)__double2loint(c.t);
         v.y = (uint32_t)__double2hiint(c.t);
         v.z = c.op == RT_NO_HIT ? RT_NO_HIT : (c.op | (c.face << 29));
-        v.w = pos;
+        v.w = pos | ((c.op == RT_NO_HIT ? 0u : c.cls) << 29); /* shade class of what was hit: k_classify needs no other load */
 #if RT_STREAM_HINTS
         __stcs(reinterpret_cast<uint4 *>(hb.rec + idx), v);
 #else
@@ -405,8 +405,7 @@ __global__ void __launch_bounds__(kThreads) k_regen(DScene sc, PathQueue q, cons
  *   class 3  Metal            class 4  Dielectric                class 5  Isotropic (ConstantMedium) */
 constexpr int kClasses = 6;
 
-__global__ void __launch_bounds__(256) k_classify(DScene sc, const uint8_t *mat_class, HitBuf hb, WaveCtl *ctl, int cur,
-                                                  uint32_t *class_idx, uint32_t cap) {
+__global__ void __launch_bounds__(256) k_classify(HitBuf hb, WaveCtl *ctl, int cur, uint32_t *class_idx, uint32_t cap) {
     uint32_t n = ctl->count[cur];
     uint32_t *class_count = ctl->class_count;
     uint32_t stride = gridDim.x * blockDim.x;
@@ -414,11 +413,7 @@ __global__ void __launch_bounds__(256) k_classify(DScene sc, const uint8_t *mat_
     for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < n; i0 += stride) {
         uint32_t i = i0 + lane;
         uint32_t cls = 0xffu;
-        if (i < n) {
-            uint32_t hop = hb.rec[i].op;
-            cls = 0;
-            if (hop != RT_NO_HIT) cls = mat_class[load_op_header(unit_ptr(sc.prog, hop & 0x1fffffffu)).z];
-        }
+        if (i < n) cls = hb.rec[i].rng >> 29; /* written by k_extend: 0 for a miss, else the class of the material that was hit */
         uint32_t peers = __match_any_sync(0xffffffffu, cls);
         if (cls != 0xffu) {
             int leader = __ffs(peers) - 1;
@@ -556,7 +551,7 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(DScene sc, PathQueue qi
             pid = rr.pid;
             left = rr.rng >> RT_POS_BITS; /* segments this path may still trace, this one included */
             rt_rng rng;
-            path_rng(rng, wp, pid, hr.rng);
+            path_rng(rng, wp, pid, hr.rng & RT_POS_MASK);
             V3 contrib = v3(0., 0., 0.);
             alive = shade_segment<CLS>(sc, r, hr.t, hr.op, rng, beta, next, contrib);
             pos = rng.pos;
@@ -800,7 +795,6 @@ struct rtgpu_scene : WaveRes {
     int device = 0;
     DScene d;
     std::vector<void *> allocs;
-    const uint8_t *mat_class = nullptr; /* device: shade class per material */
     bool class_present[8] = {true, false, false, false, false, false, false, false};
     int sort_mode = 1;          /* RTGPU_SORT_RAYS=0: never reorder rays between bounces */
     uint32_t sort_min = 1u << 18; /* RTGPU_SORT_MIN: smallest bounce worth a sort (A/B on the B200: 100 K .. 2 M within 1 %) */
@@ -920,9 +914,9 @@ rtgpu_status validate(const rtgpu_scene_desc *d) {
 
 /* The caller's program (64-byte ops, include/rtgpu.h) -> the device's 32-byte units (rt_device.cuh): a BvhNode becomes
  * ONE unit with an f32 copy of its box, its f64 box goes to boxes64[ordinal]; every other slot is copied as two units;
- * skip indices are re-mapped.  Two zero units pad the end (the walk always fetches units i and i+1). */
-rtgpu_status repack_program(const rtgpu_scene_desc *d, std::vector<uint32_t> &units, std::vector<double> &boxes64, float *extent,
-                            uint32_t *n_units) {
+ * skip indices are re-mapped; the unused skip word of a primitive gets the shade class of its material.  Two zero units pad the end (the walk always fetches units i and i+1). */
+rtgpu_status repack_program(const rtgpu_scene_desc *d, const std::vector<uint8_t> &mat_class, std::vector<uint32_t> &units,
+                            std::vector<double> &boxes64, float *extent, uint32_t *n_units) {
     std::vector<uint32_t> at((size_t)d->n_ops + 1);
     uint32_t u = 0, n_nodes = 0;
     for (uint32_t i = 0; i < d->n_ops;) {
@@ -965,6 +959,7 @@ rtgpu_status repack_program(const rtgpu_scene_desc *d, std::vector<uint32_t> &un
         } else {
             memcpy(w, &op, sizeof(rtgpu_op) * width);
             if (kind == RTGPU_OP_MEDIUM || kind == RTGPU_OP_PUSH) w[1] = at[op.skip];
+            else if (kind != RTGPU_OP_POP) w[1] = mat_class[op.a]; /* a primitive has no skip: word 1 carries the shade class of its material */
         }
         i += width;
     }
@@ -1143,7 +1138,7 @@ rtgpu_status run_paths(rtgpu_scene *s, const WaveParams &wp, const PathSink &sk,
             if (wt) wt->launches += 2;
         }
         {
-            k_classify<<<blocks, 256, 0, stream>>>(s->d, s->mat_class, s->hb, s->ctl, cur, s->class_idx, cap);
+            k_classify<<<blocks, 256, 0, stream>>>(s->hb, s->ctl, cur, s->class_idx, cap);
 #define RT_SHADE(C)                                                                                                                     \
     k_shade<C><<<kSMs * RT_SHADE_BLOCKS_PER_SM, kShadeThreads, 0, stream>>>(s->d, qin, s->hb, qout, s->ctl, cur, s->class_idx + (size_t)C * cap, sk, \
                                                                             wp, grid, sorting ? s->sort_keys[0] : nullptr)
@@ -1270,9 +1265,29 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
     if (const char *e = getenv("RTGPU_SORT_MIN")) s->sort_min = (uint32_t)atoll(e);
     memset(&s->d, 0, sizeof s->d);
     SceneArena arena;
+    /* shade class per material (see k_classify) */
+    std::vector<uint8_t> mc(desc->n_materials ? desc->n_materials : 1, 2);
+    {
+        auto simple_tex = [&](uint32_t t) {
+            const rtgpu_texture &x = desc->textures[t];
+            if (x.kind == 0) return true;
+            return x.kind == 1 && desc->textures[x.a].kind == 0 && desc->textures[x.b].kind == 0;
+        };
+        for (uint32_t i = 0; i < desc->n_materials; ++i) {
+            const rtgpu_material &m = desc->materials[i];
+            switch (m.kind) {
+            case 0: mc[i] = simple_tex(m.tex) ? 1 : 2; break;
+            case 1: mc[i] = 3; break;
+            case 2: mc[i] = 4; break;
+            case 3: mc[i] = 0; break;
+            default: mc[i] = 5; break;
+            }
+            s->class_present[mc[i]] = true;
+        }
+    }
     std::vector<uint32_t> units;
     std::vector<double> boxes64;
-    st = repack_program(desc, units, boxes64, &s->d.extent, &s->d.n_units);
+    st = repack_program(desc, mc, units, boxes64, &s->d.extent, &s->d.n_units);
     if (st != RTGPU_OK) {
         rtgpu_scene_destroy(s);
         return st;
@@ -1290,27 +1305,6 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
     arena.add(desc->images, desc->n_images, &s->d.images);
     arena.add(desc->texels, (size_t)desc->n_texel_bytes, &s->d.texels);
     arena.add(desc->lights, desc->n_lights, &s->d.lights);
-    {
-        /* shade class per material (see k_classify) */
-        std::vector<uint8_t> mc(desc->n_materials ? desc->n_materials : 1, 2);
-        auto simple_tex = [&](uint32_t t) {
-            const rtgpu_texture &x = desc->textures[t];
-            if (x.kind == 0) return true;
-            return x.kind == 1 && desc->textures[x.a].kind == 0 && desc->textures[x.b].kind == 0;
-        };
-        for (uint32_t i = 0; i < desc->n_materials; ++i) {
-            const rtgpu_material &m = desc->materials[i];
-            switch (m.kind) {
-            case 0: mc[i] = simple_tex(m.tex) ? 1 : 2; break;
-            case 1: mc[i] = 3; break;
-            case 2: mc[i] = 4; break;
-            case 3: mc[i] = 0; break;
-            default: mc[i] = 5; break;
-            }
-            s->class_present[mc[i]] = true;
-        }
-        arena.add(mc.data(), mc.size(), &s->mat_class);
-    }
     st = arena.commit(s);
     if (st != RTGPU_OK) {
         rtgpu_scene_destroy(s);

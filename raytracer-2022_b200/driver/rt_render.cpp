@@ -107,8 +107,10 @@ int main(int argc, char **argv) {
     }
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_render).count();
     printf("[3/5] Collecting results... (one reduce of %.1f MB: %.2f ms)\n", n_float * 4 / 1e6, ms_reduce);
-    printf("      %.3f s, %.1f Mrays/s, %.1f Msamples/s, %.2f rays/sample\n", sec, stats.rays / sec / 1e6, stats.samples / sec / 1e6,
-           (double)stats.rays / (double)(stats.samples ? stats.samples : 1));
+    /* device time of the slowest GPU; the wall time also holds scene upload and, with several GPUs, ncclCommInitAll (seconds) */
+    printf("      render %.3f s on the device (%.1f Mrays/s, %.1f Msamples/s, %.2f rays/sample); %.3f s wall with set-up\n", stats.ms_total * 1e-3,
+           stats.rays / (stats.ms_total * 1e3), stats.samples / (stats.ms_total * 1e3), (double)stats.rays / (double)(stats.samples ? stats.samples : 1),
+           sec);
 
     // ---- image ----
     printf("[4/5] Generating image...\n");
