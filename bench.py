@@ -271,7 +271,7 @@ def main():
     ap.add_argument("--workload", default="c3_final_scene_800x800", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=192, help="samples per pixel per step per GPU")
     ap.add_argument("--pool", type=int, default=0,
-                    help="paths kept in flight per GPU (248 B each); 0 = the library default of 12 Mi paths (3.1 GB).  Finished paths "
+                    help="paths kept in flight per GPU (248 B each); 0 = the library default of 15 Mi paths (3.9 GB).  Finished paths "
                          "are replaced by new camera rays, so every launch carries a full queue whatever the step size")
     ap.add_argument("--c5-spp", type=int, default=256, help="total samples per pixel of the config-5 (3840x2160) leg, split over the ranks")
     ap.add_argument("--no-workloads", action="store_true", help="skip the C1 / C2 / C4 / C5 legs")
@@ -346,7 +346,7 @@ def main():
         except rt.RtError as e:
             if "memory" not in str(e).lower() or (pool[0] and pool[0] <= (1 << 20)):
                 raise
-            pool[0] = max(1 << 20, (pool[0] or (12 << 20)) // 2)
+            pool[0] = max(1 << 20, (pool[0] or (15 << 20)) // 2)
             print(f"bench: pool does not fit this device, retrying with {pool[0]} paths in flight", file=sys.stderr)
     for _ in range(args.warmup - 1):
         step()

@@ -179,7 +179,7 @@ typedef struct rtgpu_render_params {
     int32_t max_depth;          /* main.rs:39 */
     int32_t device;             /* CUDA device ordinal; -1 = current */
     uint64_t seed;
-    int64_t max_paths_in_flight; /* size of the path pool (248 B of device memory per path); 0 = 12 Mi paths (3.1 GB).  Paths
+    int64_t max_paths_in_flight; /* size of the path pool (248 B of device memory per path); 0 = 15 Mi paths (3.9 GB).  Paths
                                     that end are replaced by new camera rays while samples remain (path regeneration). */
     void *stream;                /* cudaStream_t; NULL = default stream */
     int32_t accumulate;          /* 0: overwrite accum, 1: add to it */

@@ -118,8 +118,10 @@ struct TravScene {
     const rtgpu_xform *xforms;
     const uint32_t *chain;
     float extent;
+    uint32_t end; /* the walk stops at this unit: n_units, or the end of a ConstantMedium's boundary (kept here, i.e. in the parameter
+                     bank, rather than in a register of every lane) */
 };
-__device__ __forceinline__ TravScene trav_of(const DScene &sc) { return TravScene{sc.prog, sc.boxes64, sc.xforms, sc.chain, sc.extent}; }
+__device__ __forceinline__ TravScene trav_of(const DScene &sc) { return TravScene{sc.prog, sc.boxes64, sc.xforms, sc.chain, sc.extent, sc.n_units}; }
 __device__ __forceinline__ rtgpu_xform load_xform(const TravScene &sc, uint32_t chain_idx) {
     const rtgpu_xform *x = sc.xforms + __ldg(sc.chain + chain_idx);
     const double2 *p = reinterpret_cast<const double2 *>(x);
@@ -246,16 +248,22 @@ struct Closest {
  * Traversal<RayRegs> is the single-ray walk with everything in registers: it runs the boundary of a ConstantMedium
  * that is not one sphere (closest_hit_boundary).  The main walk of k_extend is extend_cta_loop below, which keeps its
  * rays in shared memory and uses the same tests phase by phase. */
-struct RayRegs {
+/* CONST_TMIN: t_min is the 0.001 of main.rs:243 for every ray (k_extend), which saves its two registers */
+template <bool CONST_TMIN>
+struct RayRegsT {
     V3 o_, d_;
     double tm_, tmin_;
     __device__ __forceinline__ V3 o() const { return o_; }
     __device__ __forceinline__ V3 d() const { return d_; }
     __device__ __forceinline__ double tm() const { return tm_; }
-    __device__ __forceinline__ double tmin() const { return tmin_; }
+    __device__ __forceinline__ double tmin() const { return CONST_TMIN ? 0.001 : tmin_; }
     __device__ __forceinline__ void set_od(V3 o, V3 d) { o_ = o; d_ = d; }
-    __device__ __forceinline__ void set_times(double tm, double tmin) { tm_ = tm; tmin_ = tmin; }
+    __device__ __forceinline__ void set_times(double tm, double tmin) {
+        tm_ = tm;
+        if (!CONST_TMIN) tmin_ = tmin;
+    }
 };
+typedef RayRegsT<false> RayRegs;
 #ifndef RT_NODE_FETCH32
 #define RT_NODE_FETCH32 0 /* 1: fetch 32 bytes for a NODE and the other 32 only for leaf ops -- fewer L1 data-pipe cycles (50 % -> 35 %)
                              but the dependent second fetch lengthens every leaf: 8 % slower on the B200 */
@@ -293,7 +301,7 @@ struct Traversal {
     CullRay c;          /* f32 view for the box pre-test (rt_cull.h) */
     float bestL, bestU; /* bestL <= best.t <= bestU */
     Closest best;
-    uint32_t i, end;
+    uint32_t i;
     int sp;
     uint4 h;     /* bytes 0..15 of unit i: header of a leaf op / kind|ordinal, skip, box min.xy of a NODE */
     double p[6]; /* bytes 16..63: payload of a leaf op / rest of the NODE box, then unit i+1 */
@@ -303,7 +311,7 @@ struct Traversal {
     /* fetched as soon as the index is known: the L1/L2 latency of the next op overlaps with the warp
      * vote and with the other lanes' work */
     __device__ __forceinline__ void fetch_op(const TravScene sc) {
-        if (i < end) {
+        if (i < sc.end) {
             const uint4 *op = unit_ptr(sc.prog, i);
             h = load_op_header(op);
             const double2 *q = reinterpret_cast<const double2 *>(op) + 1;
@@ -330,8 +338,7 @@ struct Traversal {
         /* 1/d: what AABB::hit divides per node (aabb.rs:17) */
         cull_ray_setup(c, o.x, o.y, o.z, 1. / d.x, 1. / d.y, 1. / d.z, tmin, extent);
     }
-    __device__ __forceinline__ void start(const TravScene sc, uint32_t begin, uint32_t end_, V3 o, V3 d, double tm_, double tmin_,
-                                          double tmax) {
+    __device__ __forceinline__ void start(const TravScene sc, uint32_t begin, V3 o, V3 d, double tm_, double tmin_, double tmax) {
         best.t = tmax;
         best.op = RT_NO_HIT;
         best.face = 0;
@@ -341,11 +348,10 @@ struct Traversal {
         derive(o, d, tmin_, sc.extent);
         set_best_bounds();
         i = begin;
-        end = end_;
         sp = 0;
         fetch_op(sc);
     }
-    __device__ __forceinline__ bool done() const { return i >= end; }
+    __device__ __forceinline__ bool done(const TravScene sc) const { return i >= sc.end; }
     __device__ __forceinline__ uint32_t phase() const { return phase_of_kind(h.x & 0xffu); }
     __device__ __forceinline__ bool at_node() const { return (h.x & 0xffu) == RTGPU_OP_NODE; } /* = phase() == PH_NODE, two instructions */
 
@@ -542,8 +548,10 @@ __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_
                                                      double tmin, double tmax) {
     Traversal<RayRegs> tr;
     SavedRays stk;
-    tr.start(sc, begin, end, o, d, tm, tmin, tmax);
-    while (!tr.done()) tr.step<false>(sc, stk, []() { return 0.; });
+    TravScene sub = sc;
+    sub.end = end;
+    tr.start(sub, begin, o, d, tm, tmin, tmax);
+    while (!tr.done(sub)) tr.step<false>(sub, stk, []() { return 0.; });
     return tr.best;
 }
 
@@ -584,7 +592,7 @@ __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_
 template <typename IO>
 __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_units, uint32_t n, uint32_t *fetch, IO &io) {
     const uint32_t lane = threadIdx.x & 31u;
-    Traversal<RayRegs> tr;
+    Traversal<RayRegsT<IO::kConstTmin>> tr;
     SavedRays stk;
     bool active = false, exhausted = false;
     uint32_t rng_a = 0, rng_b = 0, rng_pos = 0, cur = 0;
@@ -606,8 +614,8 @@ __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_
                     V3 o, d;
                     double tm, tmin, tmax;
                     io.load(idx, o, d, tm, tmin, tmax, rng_a, rng_b, rng_pos, cur);
-                    tr.start(ts, 0, n_units, o, d, tm, tmin, tmax);
-                    active = !tr.done();
+                    tr.start(ts, 0, o, d, tm, tmin, tmax);
+                    active = !tr.done(ts);
                     if (!active) io.store(cur, tr.best, rng_pos);
                 }
             }
@@ -618,7 +626,7 @@ __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_
          * one ballot of overhead); lanes that reached a leaf wait.  Then every waiting lane runs its
          * leaf op once (plain SIMT over the few leaf kinds) and the cycle repeats. */
         const uint32_t n_active = 32u - (uint32_t)__popc(idle);
-        const uint32_t node_quorum = max(1u, (n_active * RT_NODE_QUORUM_PCT) / 100u);
+        const uint32_t node_quorum = max(1u, (n_active * (uint32_t)((RT_NODE_QUORUM_PCT * 32 + 50) / 100)) >> 5); /* = RT_NODE_QUORUM_PCT % of the live lanes */
         bool node_ran = false;
 #pragma unroll 1
         for (;;) {
@@ -629,15 +637,15 @@ __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_
             if (in_node) {
                 tr.exec_node(ts);
 #if RT_NODE_UNROLL >= 2
-                if (!tr.done() && tr.at_node()) tr.exec_node(ts); /* second box under the same vote */
+                if (!tr.done(ts) && tr.at_node()) tr.exec_node(ts); /* second box under the same vote */
 #endif
 #if RT_NODE_UNROLL >= 3
-                if (!tr.done() && tr.at_node()) tr.exec_node(ts);
+                if (!tr.done(ts) && tr.at_node()) tr.exec_node(ts);
 #endif
 #if RT_NODE_UNROLL >= 4
-                if (!tr.done() && tr.at_node()) tr.exec_node(ts);
+                if (!tr.done(ts) && tr.at_node()) tr.exec_node(ts);
 #endif
-                if (tr.done()) {
+                if (tr.done(ts)) {
                     io.store(cur, tr.best, rng_pos);
                     active = false;
                 }
@@ -668,7 +676,7 @@ __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_
             case PH_TRI: tr.exec_tri(ts); break;
             default: tr.template exec_misc<true>(ts, stk, [&]() { return io.draw(rng_a, rng_b, rng_pos); }); break;
             }
-            if (tr.done()) {
+            if (tr.done(ts)) {
                 io.store(cur, tr.best, rng_pos);
                 active = false;
             }
