@@ -66,6 +66,7 @@ def host_lib():
         L.rtg_lowered_free.argtypes = [C.c_void_p]
         L.rtg_lowered_desc.argtypes = [C.c_void_p, C.POINTER(D.rtgpu_scene_desc)]
         L.rtg_decode_jpeg.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_size_t]
+        L.rtg_encode_jpeg.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         _host = L
     return _host
 
@@ -412,6 +413,15 @@ def multi_render(lowered, width, height, spp_begin, spp_end, n_devices, devices=
     if st != D.RTGPU_OK:
         raise RtError(f"rtgpu_multi_render: status {st}: {(G.rtgpu_last_error() or b'').decode()}")
     return accum, stats, ms.value
+
+
+def encode_jpeg(path, rgb8, quality=100):
+    """RGB8 (H x W x 3, top row first) -> baseline JPEG file; quality 100 is what main.rs:213-221 writes."""
+    L = host_lib()
+    arr = np.ascontiguousarray(rgb8, dtype=np.uint8)
+    h, w, _ = arr.shape
+    if L.rtg_encode_jpeg(os.fsencode(path), C.c_void_p(arr.ctypes.data), w, h, int(quality)) != 0:
+        raise RtError((L.rtg_last_error() or b"").decode())
 
 
 def decode_jpeg(path):

@@ -7,7 +7,7 @@
  *         render                      main.rs:93-163    rtgpu_multi_render: one host thread per GPU, spp-sharded
  *   [3/5] collect                     main.rs:171-183   ... and ONE ncclReduce(sum) of the float accumulation buffers
  *   [4/5] write_color + row flip      main.rs:191-201   rtgpu_resolve
- *   [5/5] image file                  main.rs:213-221   binary PPM (the JPEG encoder is out of scope)
+ *   [5/5] image file                  main.rs:213-221   JPEG at quality 100 (host/jpeg_encode.cpp) when --out ends in .jpg, else binary PPM
  *
  * Build: see __graft_entry__.build().  Links librthost.so and librtgpu.so (which loads NCCL at run time).
  */
@@ -44,7 +44,7 @@ bool parse(int argc, char **argv, Args &a) {
         else {
             fprintf(stderr,
                     "usage: rt_render [--scene random_scene|cornell_box|cornell_smoke|cornell_book3|final_scene|obj_cornell|wwscene]\n"
-                    "                 [--width W --height H --spp N --depth D --seed S --devices G --assets DIR --out FILE.ppm]\n");
+                    "                 [--width W --height H --spp N --depth D --seed S --devices G --assets DIR --out FILE.ppm|FILE.jpg]\n");
             return false;
         }
     }
@@ -120,14 +120,23 @@ int main(int argc, char **argv) {
         return 1;
     }
     printf("[5/5] Output image as \"%s\"\n", a.out.c_str());
-    FILE *f = fopen(a.out.c_str(), "wb");
-    if (!f) {
-        fprintf(stderr, "Outputting image fails.\n");
-        return 1;
+    auto ends_with = [&](const char *suf) { size_t n = strlen(suf); return a.out.size() >= n && a.out.compare(a.out.size() - n, n, suf) == 0; };
+    if (ends_with(".jpg") || ends_with(".jpeg")) { // main.rs:213-221: JPEG at quality 100
+        std::string err;
+        if (!rt::encode_jpeg(a.out, rgb.data(), a.width, a.height, 100, err)) {
+            fprintf(stderr, "%s\n", err.c_str());
+            return 1;
+        }
+    } else {
+        FILE *f = fopen(a.out.c_str(), "wb");
+        if (!f) {
+            fprintf(stderr, "Outputting image fails.\n");
+            return 1;
+        }
+        fprintf(f, "P6\n%d %d\n255\n", a.width, a.height);
+        fwrite(rgb.data(), 1, rgb.size(), f);
+        fclose(f);
     }
-    fprintf(f, "P6\n%d %d\n255\n", a.width, a.height);
-    fwrite(rgb.data(), 1, rgb.size(), f);
-    fclose(f);
     printf("\n      All Work Done.\n      Elapsed Time: %.2f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count());
     return 0;
 }

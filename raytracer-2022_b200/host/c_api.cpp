@@ -214,4 +214,13 @@ int rtg_decode_jpeg(const char *path, int *w, int *h, uint8_t *rgb_out, size_t c
     return 0;
 }
 
+int rtg_encode_jpeg(const char *path, const uint8_t *rgb, int w, int h, int quality) {
+    std::string err;
+    if (!rt::encode_jpeg(path, rgb, w, h, quality, err)) {
+        g_err = err;
+        return -1;
+    }
+    return 0;
+}
+
 } // extern "C"

@@ -170,6 +170,9 @@ std::vector<ObjMesh> load_obj(const std::string &path);
 /* Baseline JPEG -> RGB8, top row first (stands in for image 0.23.14 / jpeg-decoder 0.1.22) */
 bool decode_jpeg(const std::string &path, int &w, int &h, std::vector<uint8_t> &rgb, std::string &err);
 bool decode_jpeg_mem(const uint8_t *data, size_t n, int &w, int &h, std::vector<uint8_t> &rgb, std::string &err);
+/* RGB8 (top row first) -> baseline JPEG, 4:4:4, IJG quality scale; stands in for image 0.23.14's write_to(Jpeg(q)), main.rs:213-221 */
+bool encode_jpeg_mem(const uint8_t *rgb, int w, int h, int quality, std::vector<uint8_t> &out, std::string &err);
+bool encode_jpeg(const std::string &path, const uint8_t *rgb, int w, int h, int quality, std::string &err);
 
 /* ---- scene.rs ------------------------------------------------------------------------------ */
 struct SceneOptions {
@@ -247,6 +250,7 @@ void rtg_lowered_free(rtg_lowered *l);
 int rtg_lowered_desc(const rtg_lowered *l, rtgpu_scene_desc *out);
 
 int rtg_decode_jpeg(const char *path, int *w, int *h, uint8_t *rgb_out, size_t cap);
+int rtg_encode_jpeg(const char *path, const uint8_t *rgb, int w, int h, int quality);
 }
 
 #endif /* RT_HOST_H */

@@ -60,6 +60,13 @@ def test_native_driver_writes_the_same_image(tmp_path):
         px = np.frombuffer(data[len(header):], dtype=np.uint8).reshape(h, w, 3)
         if g == 1:
             assert np.array_equal(px, img)
+            # the reference's own output format: JPEG at quality 100 (main.rs:213-221)
+            jpg = tmp_path / "out1.jpg"
+            r = subprocess.run([exe, "--scene", "cornell_book3", "--width", str(w), "--height", str(h), "--spp", str(spp), "--seed", str(seed),
+                                "--devices", "1", "--assets", rt.ASSET_DIR, "--out", str(jpg)], capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stdout + r.stderr
+            dj = np.abs(rt.decode_jpeg(str(jpg)).astype(int) - img.astype(int))
+            assert dj.max() <= 6 and dj.mean() <= 1.0
         else:  # two float sums added in another order: at most one 8-bit level, on few pixels
             d = np.abs(px.astype(int) - img.astype(int))
             assert d.max() <= 1 and (d > 0).mean() < 0.01

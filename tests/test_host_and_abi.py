@@ -249,3 +249,28 @@ def test_f32_box_pretest_never_contradicts_the_f64_test(tmp_path):
     assert r.returncode == 0 and "mismatches 0" in r.stdout, r.stdout + r.stderr
     unsure = float(r.stdout.split("(")[1].split("%")[0])
     assert unsure < 40.0  # this test set lives on the decision boundary; a render sees ~0.05 % undecided boxes
+
+
+def test_jpeg_writer_quality_100_roundtrip(tmp_path):
+    """The output stage of main.rs:213-221 (JPEG at quality 100): host/jpeg_encode.cpp writes a baseline 4:4:4 stream that
+    both this repo's decoder and libjpeg-turbo (PIL) read back to within 4 levels of the input (YCbCr rounding; every
+    quantiser is 1 at quality 100), also for sizes that are not multiples of 8 and for a real image."""
+    from PIL import Image
+    rng = np.random.default_rng(5)
+    yy, xx = np.mgrid[0:77, 0:101]
+    synth = np.stack([(xx * 2.5) % 256, (yy * 3.1) % 256, ((xx + yy) * 1.7) % 256], -1).astype(np.uint8)
+    synth[20:40, 30:60] = rng.integers(0, 256, (20, 30, 3))
+    earth = rt.decode_jpeg(os.path.join(rt.ASSET_DIR, "earthmap.jpg"))[100:228, 300:491]
+    for k, img in enumerate((synth, earth, np.full((8, 8, 3), 200, np.uint8), np.zeros((1, 1, 3), np.uint8))):
+        path = str(tmp_path / f"t{k}.jpg")
+        rt.encode_jpeg(path, img, 100)
+        own = rt.decode_jpeg(path)
+        pil = np.array(Image.open(path).convert("RGB"))
+        assert own.shape == img.shape == pil.shape
+        for dec in (own, pil):
+            d = np.abs(dec.astype(int) - img.astype(int))
+            assert d.max() <= 4 and d.mean() <= 0.7, (k, d.max(), d.mean())
+    rt.encode_jpeg(str(tmp_path / "q50.jpg"), synth, 50)  # the IJG quality scale: lower quality, smaller file
+    assert os.path.getsize(tmp_path / "q50.jpg") < 0.5 * os.path.getsize(tmp_path / "t0.jpg")
+    with pytest.raises(rt.RtError):
+        rt.encode_jpeg("/nonexistent-dir/x.jpg", synth, 100)
