@@ -105,7 +105,7 @@ if os.path.exists(f"{G}/prof_extend_steady.ncu-rep"):
                     pass
         cols.append(("iteration 16 (steady state of the regenerating pool: 38 % new camera rays, the rest from bounces 1..15)", row))
 with open(f"{out_dir}/{tag}_k_extend_ncu.txt", "w") as f:
-    f.write("# ncu --set full --clock-control none --import-source on -k regex:k_extend -s 92 -c 2   (and -s 106 -c 1)\n")
+    f.write("# ncu --set full --clock-control none --import-source on -k regex:k_extend -s 81 -c 2   (and -s 95 -c 1)\n")
     f.write("# launches of the timed step of: python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-workloads\n")
     f.write("# columns: " + " | ".join(n for n, _ in cols) + "\n")
     for w in want:
