@@ -62,7 +62,6 @@ constexpr int kThreads = RT_THREADS;
 #endif
 constexpr int kShadeThreads = RT_SHADE_THREADS;
 
-constexpr int kSMs = 148;
 #ifndef RT_BLOCKS_PER_SM
 #define RT_BLOCKS_PER_SM 8
 #endif
@@ -795,6 +794,7 @@ struct WaveRes {
 
 struct rtgpu_scene : WaveRes {
     int device = 0;
+    int n_sm = 148; /* multiprocessors of the device (cudaDevAttrMultiProcessorCount) */
     DScene d;
     std::vector<void *> allocs;
     bool class_present[8] = {true, false, false, false, false, false, false, false};
@@ -987,7 +987,7 @@ rtgpu_status SceneArena::commit(rtgpu_scene *s) {
     return RTGPU_OK;
 }
 
-int grid_blocks() { return kSMs * kBlocksPerSM; }
+int grid_blocks(const rtgpu_scene *s) { return s->n_sm * kBlocksPerSM; } /* persistent grids: a multiple of the SM count (148 on a B200) */
 
 constexpr size_t kBytesPerPath = 2 * (sizeof(RayRec) + sizeof(StateRec)) + sizeof(HitRec16) + 4 * 4 + kClasses * 4; /* 248 */
 
@@ -1079,7 +1079,7 @@ rtgpu_status run_paths(rtgpu_scene *s, const WaveParams &wp, const PathSink &sk,
     if (st != RTGPU_OK) return st;
     if (wp.n_paths == 0 || wp.max_depth == 0) return RTGPU_OK; /* depth 0: every ray_color call returns black (main.rs:240-242) */
     CK(cudaMemsetAsync(s->ctl, 0, sizeof(WaveCtl), stream));
-    const int blocks = grid_blocks();
+    const int blocks = grid_blocks(s);
     const uint32_t cap = (uint32_t)s->cap;
     bool sorting = s->sort_mode != 0 && wp.n_paths >= s->sort_min && wp.max_depth > 1;
     SortGrid *grid = reinterpret_cast<SortGrid *>(s->sort_bounds + 8);
@@ -1142,7 +1142,7 @@ rtgpu_status run_paths(rtgpu_scene *s, const WaveParams &wp, const PathSink &sk,
         {
             k_classify<<<blocks, 256, 0, stream>>>(s->hb, s->ctl, cur, s->class_idx, cap);
 #define RT_SHADE(C)                                                                                                                     \
-    k_shade<C><<<kSMs * RT_SHADE_BLOCKS_PER_SM, kShadeThreads, 0, stream>>>(s->d, qin, s->hb, qout, s->ctl, cur, s->class_idx + (size_t)C * cap, sk, \
+    k_shade<C><<<s->n_sm * RT_SHADE_BLOCKS_PER_SM, kShadeThreads, 0, stream>>>(s->d, qin, s->hb, qout, s->ctl, cur, s->class_idx + (size_t)C * cap, sk, \
                                                                             wp, grid, sorting ? s->sort_keys[0] : nullptr)
             int n_launched = 0;
             RT_SHADE(0);
@@ -1255,6 +1255,10 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
     rtgpu_scene *s = new (std::nothrow) rtgpu_scene();
     if (!s) return RTGPU_ERR_OOM;
     s->device = cur;
+    if (cudaDeviceGetAttribute(&s->n_sm, cudaDevAttrMultiProcessorCount, cur) != cudaSuccess || s->n_sm < 1) {
+        cudaGetLastError();
+        s->n_sm = 148;
+    }
     {
         std::lock_guard<std::mutex> lock(g_park_mutex);
         if (cur >= 0 && cur < kMaxDevices && g_parked_valid[cur]) {
@@ -1485,9 +1489,9 @@ rtgpu_status rtgpu_trace_batch(rtgpu_scene *s, const rtgpu_ray *rays, int64_t n,
         CK(cudaEventCreate(&e0));
         CK(cudaEventCreate(&e1));
         CK(cudaEventRecord(e0, 0));
-        k_trace_extend<<<grid_blocks(), kThreads>>>(s->d, d_rays, d_keys, d_t, d_u32, d_u32 + n, (uint32_t)n, d_u32 + 2 * n);
+        k_trace_extend<<<grid_blocks(s), kThreads>>>(s->d, d_rays, d_keys, d_t, d_u32, d_u32 + n, (uint32_t)n, d_u32 + 2 * n);
         CK(cudaEventRecord(e1, 0));
-        k_trace_record<<<grid_blocks(), kThreads>>>(s->d, d_rays, d_t, d_u32, d_u32 + n, d_out, (uint32_t)n);
+        k_trace_record<<<grid_blocks(s), kThreads>>>(s->d, d_rays, d_t, d_u32, d_u32 + n, d_out, (uint32_t)n);
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
         float ms = 0;
