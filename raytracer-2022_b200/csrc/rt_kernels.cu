@@ -621,6 +621,85 @@ __global__ void k_finish(PathSink sk, float *accum, uint32_t npix, int add) {
     }
 }
 
+/* The tail of a render: once every path has been generated and only a few thousand are still alive, another 30 - 45 iterations
+ * of ~12 launches each would carry a few thousand rays apiece (0.2 - 0.3 ms per iteration for nothing).  k_tail finishes those
+ * paths in ONE launch: a thread takes a queue entry and runs its path to the end -- the single-ray walk of the traversal program
+ * (the same Traversal::step the medium boundaries use) and the same shade_segment<class>() as the class kernels, so every path
+ * gets bit for bit what the iterations would have given it. */
+__global__ void __launch_bounds__(kThreads) k_tail(DScene sc, PathQueue q, WaveCtl *ctl, int cur, PathSink sk, WaveParams wp) {
+    const uint32_t n = ctl->count[cur];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const TravScene ts = trav_of(sc);
+    unsigned long long my_rays = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        RayRec rr = ld_ray(q.ray + i);
+        Ray r;
+        r.o = v3(rr.ox, rr.oy, rr.oz);
+        r.d = v3(rr.dx, rr.dy, rr.dz);
+        r.tm = rr.tm;
+        V3 beta = ld_beta(q.st + i);
+        const uint32_t pid = rr.pid;
+        uint32_t left = rr.rng >> RT_POS_BITS, pos = rr.rng & RT_POS_MASK;
+        V3 contrib = v3(0., 0., 0.);
+        for (;;) {
+            /* world.hit(r, 0.001, f64::MAX), main.rs:243 */
+            Traversal<RayRegs> tr;
+            SavedRays stk;
+            tr.start(ts, 0, r.o, r.d, r.tm, 0.001, RT_F64_MAX);
+            while (!tr.done(ts)) {
+                tr.step<true>(ts, stk, [&]() {
+                    rt_rng g;
+                    path_rng(g, wp, pid, pos);
+                    double u = g.gen();
+                    pos = g.pos;
+                    return u;
+                });
+            }
+            ++my_rays;
+            const uint32_t hop = tr.best.op == RT_NO_HIT ? RT_NO_HIT : (tr.best.op | (tr.best.face << 29));
+            const uint32_t cls = tr.best.op == RT_NO_HIT ? 0u : tr.best.cls;
+            rt_rng rng;
+            path_rng(rng, wp, pid, pos);
+            Ray next;
+            bool alive;
+            contrib = v3(0., 0., 0.);
+            switch (cls) {
+            case 0: alive = shade_segment<0>(sc, r, tr.best.t, hop, rng, beta, next, contrib); break;
+            case 1: alive = shade_segment<1>(sc, r, tr.best.t, hop, rng, beta, next, contrib); break;
+            case 2: alive = shade_segment<2>(sc, r, tr.best.t, hop, rng, beta, next, contrib); break;
+            case 3: alive = shade_segment<3>(sc, r, tr.best.t, hop, rng, beta, next, contrib); break;
+            case 4: alive = shade_segment<4>(sc, r, tr.best.t, hop, rng, beta, next, contrib); break;
+            default: alive = shade_segment<5>(sc, r, tr.best.t, hop, rng, beta, next, contrib); break;
+            }
+            pos = rng.pos;
+            if (alive && left <= 1u) { /* depth exhausted: the next ray_color call returns black (main.rs:240-242) */
+                alive = false;
+                contrib = v3(0., 0., 0.);
+            }
+            if (!alive) break;
+            r = next;
+            --left;
+        }
+        const uint32_t traced = wp.max_depth - left + 1u;
+        if (sk.cx) {
+            sk.cx[pid] = contrib.x;
+            sk.cy[pid] = contrib.y;
+            sk.cz[pid] = contrib.z;
+            if (sk.path_len) sk.path_len[pid] = traced;
+        } else {
+            uint32_t pixel = pid % wp.npix_wave;
+            sink_add(sk, pixel, 0, contrib.x);
+            sink_add(sk, pixel, 1, contrib.y);
+            sink_add(sk, pixel, 2, contrib.z);
+        }
+        atomicAdd(&ctl->len_hist[traced < RTGPU_MAX_BOUNCE_STATS ? traced : RTGPU_MAX_BOUNCE_STATS], 1ull);
+    }
+    /* rays traced here (the iterations count theirs in k_regen_commit) */
+    for (int o = 16; o > 0; o >>= 1) my_rays += __shfl_xor_sync(0xffffffffu, my_rays, o);
+    if ((threadIdx.x & 31) == 0 && my_rays) atomicAdd(&ctl->rays, my_rays);
+}
+__global__ void k_tail_done(WaveCtl *ctl, int cur) { ctl->count[cur] = 0; }
+
 /* dumped-ray batch: BvhNode::hit through the SAME warp loop as k_extend, then the record of the winner */
 struct BatchIO {
     static constexpr bool kConstTmin = false; /* a dumped ray brings its own t_min */
@@ -798,6 +877,7 @@ struct rtgpu_scene : WaveRes {
     DScene d;
     std::vector<void *> allocs;
     bool class_present[8] = {true, false, false, false, false, false, false, false};
+    uint32_t tail_max = 1u << 16; /* RTGPU_TAIL_MAX: at most this many live paths are finished by k_tail in one launch (0 = never) */
     int sort_mode = 1;          /* RTGPU_SORT_RAYS=0: never reorder rays between bounces */
     uint32_t sort_min = 1u << 18; /* RTGPU_SORT_MIN: smallest bounce worth a sort (A/B on the B200: 100 K .. 2 M within 1 %) */
 };
@@ -1074,7 +1154,7 @@ struct WaveTiming {
 /* Traces wp.n_paths paths with at most wp.pool of them in flight; radiance goes to `sk`.  Everything is enqueued on
  * `stream`; the host only looks at asynchronous snapshots of the control block to know when to stop. */
 rtgpu_status run_paths(rtgpu_scene *s, const WaveParams &wp, const PathSink &sk, cudaStream_t stream, bool timing, WaveTiming *wt,
-                       uint64_t *rays, uint64_t *rays_per_bounce) {
+                       uint64_t *rays, uint64_t *rays_per_bounce, bool allow_tail) {
     rtgpu_status st = ensure_pool(s, wp.pool);
     if (st != RTGPU_OK) return st;
     if (wp.n_paths == 0 || wp.max_depth == 0) return RTGPU_OK; /* depth 0: every ray_color call returns black (main.rs:240-242) */
@@ -1104,14 +1184,25 @@ rtgpu_status run_paths(rtgpu_scene *s, const WaveParams &wp, const PathSink &sk,
     /* upper bound of the number of survivors that enter the coming iteration, as far as the host knows */
     uint32_t bound = wp.pool < wp.n_paths ? wp.pool : wp.n_paths;
     bool gen_done = false; /* host knows that every path has been generated */
+    uint64_t alive_ub = wp.n_paths; /* paths that can still be alive, as far as the host knows (an upper bound) */
     const uint64_t max_iter = (uint64_t)wp.n_paths / (bound ? bound : 1) * (uint64_t)wp.max_depth + 2ull * wp.max_depth + 64;
     int cur = 0;
     uint64_t it = 0, seen = 0;
-    bool finished = false;
+    bool finished = false, tail_ran = false;
     std::vector<int> phase_of_event; /* 0 other, 1 extend, 2 shade: what ran between event k and k+1 */
     for (; it < max_iter && !finished; ++it) {
         PathQueue &qin = s->q[cur], &qout = s->q[cur ^ 1];
         if ((st = mark()) != RTGPU_OK) return st;
+        if (allow_tail && gen_done && alive_ub <= s->tail_max && it > 0) { /* the few paths that are left run to their end in one launch */
+            k_tail<<<blocks, kThreads, 0, stream>>>(s->d, qin, s->ctl, cur, sk, wp);
+            k_tail_done<<<1, 1, 0, stream>>>(s->ctl, cur);
+            CK(cudaGetLastError());
+            if (wt) wt->launches += 2;
+            phase_of_event.push_back(0);
+            finished = true;
+            tail_ran = true;
+            break;
+        }
         k_iter_begin<<<1, 32, 0, stream>>>(s->ctl, cur);
         if (!gen_done) {
             k_regen<<<blocks, kThreads, 0, stream>>>(s->d, qin, s->ctl, cur, wp);
@@ -1176,6 +1267,7 @@ rtgpu_status run_paths(rtgpu_scene *s, const WaveParams &wp, const PathSink &sk,
              * generated; in the steady state of a regenerating pool about what the last known iteration carried.  This only
              * sizes the sort: survivors beyond it are walked in place, like the new camera rays, and the result is the same. */
             uint64_t b2 = (uint64_t)survivors + left;
+            alive_ub = b2;
             if (b2 > wp.pool) b2 = wp.pool;
             uint64_t est = (uint64_t)survivors + survivors / 16 + 1024;
             bound = (uint32_t)(est < b2 ? est : b2);
@@ -1187,6 +1279,7 @@ rtgpu_status run_paths(rtgpu_scene *s, const WaveParams &wp, const PathSink &sk,
         wt->launches_extend += it;
         wt->iterations += it;
     }
+    (void)tail_ran;
     CK(cudaGetLastError());
     if ((st = mark()) != RTGPU_OK) return st;
     CK(cudaMemcpyAsync(s->ctl_host, s->ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, stream));
@@ -1269,6 +1362,7 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
     }
     if (const char *e = getenv("RTGPU_SORT_RAYS")) s->sort_mode = atoi(e);
     if (const char *e = getenv("RTGPU_SORT_MIN")) s->sort_min = (uint32_t)atoll(e);
+    if (const char *e = getenv("RTGPU_TAIL_MAX")) s->tail_max = (uint32_t)atoll(e);
     memset(&s->d, 0, sizeof s->d);
     SceneArena arena;
     /* shade class per material (see k_classify) */
@@ -1426,7 +1520,7 @@ rtgpu_status rtgpu_render(rtgpu_scene *s, const rtgpu_render_params *p, float *a
         wp.height = p->height;
         wp.max_depth = (uint32_t)p->max_depth;
         wp.pool = (uint32_t)(pool < wp.n_paths ? pool : wp.n_paths);
-        st = run_paths(s, wp, sk, stream, stats != nullptr, &wt, &rays, per_bounce);
+        st = run_paths(s, wp, sk, stream, stats != nullptr, &wt, &rays, per_bounce, true);
         if (st != RTGPU_OK) return st;
         k_finish<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(sk, acc_dev, (uint32_t)npix, (first && !p->accumulate) ? 0 : 1);
         wt.launches += 1;
@@ -1571,7 +1665,7 @@ rtgpu_status rtgpu_sample_radiance(rtgpu_scene *s, int32_t width, int32_t height
     sk.path_len = s->path_len;
     CK(cudaMemsetAsync(s->perpath_mem, 0, (size_t)s->perpath_cap * 28, 0));
     uint64_t rays = 0;
-    st = run_paths(s, wp, sk, 0, false, nullptr, &rays, nullptr);
+    st = run_paths(s, wp, sk, 0, false, nullptr, &rays, nullptr, false); /* the parity entry point stays on the class kernels */
     if (st != RTGPU_OK) return st;
     std::vector<double> tmp((size_t)n * 3);
     CK(cudaMemcpy(tmp.data(), s->cx, (size_t)n * 8, cudaMemcpyDeviceToHost));

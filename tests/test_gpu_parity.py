@@ -258,6 +258,28 @@ def test_sorted_bounce_rays_give_the_same_image(name, monkeypatch):
     assert np.array_equal(a0, a1)
 
 
+@pytest.mark.parametrize("name", ["final_scene", "random_scene", "cornell_smoke"])
+def test_tail_kernel_gives_the_same_image(name, monkeypatch):
+    """Once every path has been generated and at most 2^16 are alive, k_tail runs them to their end in one launch (single-ray
+    walk + the same shade_segment<class>() as the class kernels).  The accumulation buffer, the ray count and the rays per bounce
+    must be BIT-identical to the render that finishes through iterations (RTGPU_TAIL_MAX=0), also when the tail takes over early."""
+    s, orc, _ = get(name)
+    w, h, spp = 160, 120, 6
+    out = {}
+    for mode, env in (("iterations", "0"), ("tail", "65536"), ("early tail", "1000000")):
+        monkeypatch.setenv("RTGPU_TAIL_MAX", env)
+        gpu = rt.GpuScene(s.lower(), device=0)  # the switch is read when the scene is created
+        out[mode] = gpu.render(w, h, 0, spp, seed=21)
+        gpu.close()
+    monkeypatch.delenv("RTGPU_TAIL_MAX")
+    (a0, st0) = out["iterations"]
+    for mode in ("tail", "early tail"):
+        a1, st1 = out[mode]
+        assert st0.rays == st1.rays and list(st0.rays_per_bounce) == list(st1.rays_per_bounce)
+        assert np.array_equal(a0, a1)
+        assert st1.launches_extend < st0.launches_extend
+
+
 def test_render_matches_oracle_image_and_is_deterministic():
     s, orc, gpu = get("cornell_box")
     w = h = 48
