@@ -824,7 +824,7 @@ struct CtlSnapshot { /* what the host reads back, asynchronously, once per itera
     uint32_t count[2], gen_next, fetch;
 };
 constexpr int kSnapRing = 64;
-constexpr int kRunAhead = 2;
+constexpr int kRunAheadDefault = 2;
 struct WaveRes {
     size_t cap = 0; /* paths the pool can hold */
     void *wave_mem = nullptr;
@@ -877,6 +877,7 @@ struct rtgpu_scene : WaveRes {
     DScene d;
     std::vector<void *> allocs;
     bool class_present[8] = {true, false, false, false, false, false, false, false};
+    int run_ahead = kRunAheadDefault; /* RTGPU_RUN_AHEAD: iterations the host may be ahead of the device (1 .. 32) */
     uint32_t tail_max = 1u << 16; /* RTGPU_TAIL_MAX: at most this many live paths are finished by k_tail in one launch (0 = never) */
     int sort_mode = 1;          /* RTGPU_SORT_RAYS=0: never reorder rays between bounces */
     uint32_t sort_min = 1u << 18; /* RTGPU_SORT_MIN: smallest bounce worth a sort (A/B on the B200: 100 K .. 2 M within 1 %) */
@@ -1256,7 +1257,7 @@ rtgpu_status run_paths(rtgpu_scene *s, const WaveParams &wp, const PathSink &sk,
             const int sl = (int)(seen % kSnapRing);
             /* the host stays at most kRunAhead iterations ahead of the device: the queue bound it sizes the sort with stays
              * fresh and a finished render is not followed by a long tail of empty launches; the device always has work queued */
-            cudaError_t q = (it - seen >= (uint64_t)kRunAhead) ? cudaEventSynchronize(s->snap_ev[sl]) : cudaEventQuery(s->snap_ev[sl]);
+            cudaError_t q = (it - seen >= (uint64_t)s->run_ahead) ? cudaEventSynchronize(s->snap_ev[sl]) : cudaEventQuery(s->snap_ev[sl]);
             if (q == cudaErrorNotReady) break;
             CK(q);
             const CtlSnapshot &sn = s->snap_host[sl];
@@ -1363,6 +1364,10 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
     if (const char *e = getenv("RTGPU_SORT_RAYS")) s->sort_mode = atoi(e);
     if (const char *e = getenv("RTGPU_SORT_MIN")) s->sort_min = (uint32_t)atoll(e);
     if (const char *e = getenv("RTGPU_TAIL_MAX")) s->tail_max = (uint32_t)atoll(e);
+    if (const char *e = getenv("RTGPU_RUN_AHEAD")) {
+        int v = atoi(e);
+        s->run_ahead = v < 1 ? 1 : (v > 32 ? 32 : v);
+    }
     memset(&s->d, 0, sizeof s->d);
     SceneArena arena;
     /* shade class per material (see k_classify) */
