@@ -459,7 +459,7 @@ def main():
             "roofline": {
                 "bound": "hbm", "kernel": "k_extend", "achieved": ext_gbs, "peak": peak, "unit": "GB/s",
                 "frac": (ext_gbs / peak) if ext_gbs else None, "traffic": traffic, "peak_source": peak_src,
-                "traffic_note": (f"ncu dram bytes of ONE captured launch with {traffic_rays} rays (bounce 1 of a wave); its algorithmic "
+                "traffic_note": (f"ncu dram bytes of ONE captured launch with {traffic_rays} rays (second iteration of a step: a full pool); its algorithmic "
                                  f"bytes are {traffic_rays * EXTEND_BYTES_PER_RAY}" if traffic_rays else None),
                 "bytes_per_ray": EXTEND_BYTES_PER_RAY, "avg_launch_ms": ms_extend / max(launches_extend, 1),
                 "rays_per_launch": rays / max(launches_extend, 1),

@@ -210,7 +210,10 @@ rtgpu_status rtgpu_scene_destroy(rtgpu_scene *scene);
 
 /* Renders sample indices [spp_begin, spp_end) of every pixel and writes (or adds) the
  * per-pixel RGB radiance SUMS -- not averages; main.rs:150 -- to accum: 3*width*height
- * floats, pixel (x, y) at (y*width + x)*3, y up as in v = (y + xi)/(H-1) (main.rs:147). */
+ * floats, pixel (x, y) at (y*width + x)*3, y up as in v = (y + xi)/(H-1) (main.rs:147).
+ * Precision: upstream sums a pixel's samples in f64; here every sample is added as an exact 64-bit fixed-point
+ * integer (2^-32 units), so the sum of this call is exact to 2^-33 per sample in any order -- the image is
+ * bit-reproducible and does not depend on max_paths_in_flight -- and is rounded ONCE to the float32 buffer. */
 rtgpu_status rtgpu_render(rtgpu_scene *scene, const rtgpu_render_params *params, float *accum,
                           rtgpu_stats *stats);
 
@@ -225,7 +228,8 @@ rtgpu_status rtgpu_camera_rays(rtgpu_scene *scene, int32_t width, int32_t height
                                int64_t n, int32_t k, uint64_t seed, rtgpu_ray *out, uint32_t *rng_pos);
 
 /* One-sample radiance ray_color(...) of pixels [first_pixel, first_pixel+n), sample k, in f64.
- * Debug/parity entry point: same kernels as rtgpu_render, one wave.  out_rgb: 3*n doubles. */
+ * Debug/parity entry point: same kernels as rtgpu_render (the n paths are all in flight at once; k_tail is not used).
+ * out_rgb: 3*n doubles; out_rays (may be NULL): segments traced per path. */
 rtgpu_status rtgpu_sample_radiance(rtgpu_scene *scene, int32_t width, int32_t height, int64_t first_pixel,
                                    int64_t n, int32_t k, int32_t max_depth, uint64_t seed, double *out_rgb,
                                    uint32_t *out_rays);

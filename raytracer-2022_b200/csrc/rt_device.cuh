@@ -1,15 +1,16 @@
 /*
  * rt_device.cuh -- device-side restatement of the reference's geometry, materials, textures
- * and pdfs for sm_100a.  Everything is f64 with the reference's operation order and is
+ * and pdfs for sm_100a.  Everything that decides something is f64 with the reference's operation order,
  * compiled with -fmad=false (rustc never contracts a*b+c), so hit/miss decisions and
- * primitive ids are bit-identical to BvhNode::hit (hittable/bvh/mod.rs:86-101).
+ * primitive ids are bit-identical to BvhNode::hit (hittable/bvh/mod.rs:86-101); the one f32 computation, the
+ * pre-test of BvhNode boxes, only answers when the f64 answer is certain (rt_cull.h).
  *
  * Layout of the scene in HBM: see include/rtgpu.h for what the caller hands over.  On the device the traversal
  * program is re-packed into 32-byte UNITS (rtgpu_scene_create, rt_kernels.cu):
  *     BvhNode   1 unit : kind | ordinal << 8, skip, f32 box (min.xyz, max.xyz); its f64 box lives in boxes64[ordinal]
  *     any other 2 units: the caller's 64-byte op (two-slot ops: 4 units), skip re-mapped to units
  * A thread fetches units i and i+1 with four 128-bit loads: a whole leaf op, or a BvhNode together with whatever
- * follows it -- its left child, which is tested under the same fetch when it is a BvhNode too.  Boxes are decided
+ * follows it (RT_NODE_PAIR = 1 also tests that unit when it is a BvhNode too: measured slower, off).  Boxes are decided
  * by the f32 pre-test of rt_cull.h and, when that is not certain, by the f64 test on the f64 box.
  */
 #pragma once

@@ -17,6 +17,7 @@
  *                 (ballot + popc prefix) -- the compaction between bounces; a path that ends adds its radiance to
  *                 its pixel
  *
+ * Once every path has been generated and only a few thousand are alive, k_tail runs them to their end in one launch.
  * Queue lengths, the sample cursor and the ray counters live in a control block on the device (WaveCtl); the host
  * reads a 32-byte snapshot of it asynchronously every iteration and only uses it to stop issuing iterations.
  * Pixel sums are exact: every contribution is added as a 64-bit fixed-point integer (2^-32 units), so the sum does
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, RT_EXTEND_MIN_BLOCKS) k_extend(DScen
  *   - cub::DeviceRadixSort sorts (key, entry index) pairs;
  *   - k_extend takes its rays through the sorted index (QueueIO::perm) and writes its results to the entry's own
  *     slot, so classify / shade are unaffected and the image does not depend on the order at all.
- * The grid of origin cells is fixed per wave from the first hit points (mean +- 2.5 sigma per axis: the global fog
+ * The grid of origin cells is fixed per render from the first hit points (mean +- 2.5 sigma per axis: the global fog
  * scatters a few rays very far away; min/max bounds would waste the key bits on empty space). */
 struct SortGrid {
     float lo[3], inv[3];

@@ -285,7 +285,7 @@ def test_render_matches_oracle_image_and_is_deterministic():
     w = h = 48
     spp = 16
     a1, st1 = gpu.render(w, h, 0, spp, seed=5)
-    a2, st2 = gpu.render(w, h, 0, spp, seed=5, max_paths_in_flight=w * h * 3)  # several waves
+    a2, st2 = gpu.render(w, h, 0, spp, seed=5, max_paths_in_flight=w * h * 3)  # a pool of 3 spp: refilled five times
     assert np.array_equal(a1, a2) or np.allclose(a1, a2, rtol=1e-6, atol=1e-6)
     a3, _ = gpu.render(w, h, 0, spp, seed=5)
     assert np.array_equal(a1, a3)  # bit-reproducible
