@@ -1483,6 +1483,10 @@ rtgpu_status rtgpu_render(rtgpu_scene *s, const rtgpu_render_params *p, float *a
     /* one pass covers at most 32768 samples per pixel (the fixed-point pixel sums cannot overflow) and < 2^32 paths */
     size_t spp_per_pass = 0xfffffff0u / npix;
     if (spp_per_pass > 32768) spp_per_pass = 32768;
+    if (const char *e = getenv("RTGPU_SPP_PER_PASS")) { /* tests: several passes on a small image */
+        long long v = atoll(e);
+        if (v >= 1 && (size_t)v < spp_per_pass) spp_per_pass = (size_t)v;
+    }
     if (spp_per_pass < 1) spp_per_pass = 1;
 
     float *acc_dev = accum;

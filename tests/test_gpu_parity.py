@@ -280,6 +280,21 @@ def test_tail_kernel_gives_the_same_image(name, monkeypatch):
         assert st1.launches_extend < st0.launches_extend
 
 
+def test_many_samples_run_in_several_passes(monkeypatch):
+    """A render call covers its sample range in passes of at most 32768 spp and fewer than 2^32 paths (C5 at 10 000 spp: 20 passes of
+    517 spp); every pass adds its exact pixel sums to the caller's buffer.  Forced to 3 spp per pass on a small image: the same
+    rays, and the float sums agree with the single-pass render to float rounding (four float additions instead of one)."""
+    s, orc, gpu = get("cornell_book3")
+    w, h, spp = 96, 64, 10
+    a1, st1 = gpu.render(w, h, 0, spp, seed=3)
+    monkeypatch.setenv("RTGPU_SPP_PER_PASS", "3")
+    a2, st2 = gpu.render(w, h, 0, spp, seed=3)
+    monkeypatch.delenv("RTGPU_SPP_PER_PASS")
+    assert st1.rays == st2.rays and st1.samples == st2.samples == w * h * spp
+    assert list(st1.rays_per_bounce) == list(st2.rays_per_bounce)
+    assert np.allclose(a1, a2, rtol=2e-6, atol=1e-6)
+
+
 def test_render_matches_oracle_image_and_is_deterministic():
     s, orc, gpu = get("cornell_box")
     w = h = 48
