@@ -58,6 +58,7 @@ enum rtgpu_op_kind {
     RTGPU_OP_TRI = 7,      /* 2 slots: d = a(3) b(3) | c(3) n(3); n = unit normal,
                               precomputed with triangle.rs:30-32's operation order         */
     RTGPU_OP_MEDIUM = 8,   /* d[0] = -1/density; boundary = ops [i+1, skip)                */
+                           /* (a boundary may itself hold ONE more level of MEDIUM ops, not two)  */
     RTGPU_OP_PUSH = 9,     /* enter wrappers xforms[chain[a .. a+b)] (outermost first)     */
     RTGPU_OP_POP = 10,     /* leave them: restore the ray saved by the matching PUSH       */
     RTGPU_OP_RING = 11     /* d = dis_min dis_max: (r-t)^2, (r+t)^2, annulus in the plane y = 0 (ring.rs)  */

@@ -243,7 +243,9 @@ struct Closest {
 /* Walks units [begin, end) in order -- the reference's left-then-right recursion unrolled
  * (SURVEY.md 2.5).  The loop is "while-while": a tight run over consecutive NODE units, then one
  * leaf op, so that the lanes of a warp spend most iterations in the same code.
- * MAIN = false is the boundary walk of a ConstantMedium (no nested media, no rng).
+ * LEVEL 0 is the walk of the world; LEVEL 1 the walk of a ConstantMedium's boundary, LEVEL 2 the boundary of a ConstantMedium that
+ * sits inside another one's boundary (upstream's ConstantMedium<H> takes any Hittable, constantmedium.rs:14-43): a medium met on
+ * LEVEL 1 draws from the same stream, in visiting order; deeper nesting is refused when the scene is created.
  * `rng` draws the medium's free path (constantmedium.rs:60) in visiting order.
  *
  * Traversal<RayRegs> is the single-ray walk with everything in registers: it runs the boundary of a ConstantMedium
@@ -274,8 +276,32 @@ typedef RayRegsT<false> RayRegs;
                           second test is wasted whenever the first box is missed) */
 #endif
 
-__device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm,
-                                                     double tmin, double tmax);
+#define RT_MAX_MEDIUM_NESTING 2 /* a ConstantMedium inside the boundary of a ConstantMedium, and no deeper (kernels: NEST 1, 2) */
+/* Where a walk draws its uniforms from: a VALUE type with `double operator()()` and a stream position `pos`.  It is handed to
+ * the out-of-line boundary walk by value and the position comes back in the result: taking the address of the caller's state
+ * would push it into local memory for the whole kernel. */
+/* result of a boundary walk: t and op as usual; `face` carries the stream position after the walk (a boundary's box side is
+ * never needed), so that the result stays a plain register-returned Closest */
+typedef Closest BoundaryHit;
+/* a fully resolved Philox slot stream (include/rt_rng.h): 24 bytes, cheap to pass by value */
+struct StreamDraw {
+    uint64_t seed;
+    uint32_t s0, s1, domain, pos;
+    __device__ __forceinline__ double operator()() {
+        rt_rng g;
+        g.init(seed, s0, s1, domain, pos);
+        double u = g.gen();
+        pos = g.pos;
+        return u;
+    }
+    __device__ __forceinline__ StreamDraw stream() const { return *this; }
+};
+/* NEST = how many levels of ConstantMedium boundaries the instantiation walks.  Kernels exist for NEST 1 and 2: the mere presence
+ * of the LEVEL 2 walk behind the out-of-line call makes ptxas keep the warp loop's state in local memory (k_extend 2x slower,
+ * measured), so scenes without a medium inside a medium's boundary -- all of the reference's -- run the NEST 1 kernels. */
+template <int LEVEL, int NEST>
+__device__ __noinline__ BoundaryHit closest_hit_boundary(const TravScene sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm,
+                                                         double tmin, double tmax, StreamDraw ds);
 
 /* phases of the warp scheduler: ops whose code is the same run together */
 enum { PH_NODE = 0, PH_SPHERE = 1, PH_BOX = 2, PH_TRI = 3, PH_MISC = 4, PH_EXACT = 5, PH_NONE = 7 };
@@ -429,8 +455,8 @@ struct Traversal {
         fetch_op(sc);
     }
     /* rects, ConstantMedium, PUSH, POP.  DRAW() = next uniform of the ray's stream */
-    template <bool MAIN, typename DRAW>
-    __device__ __forceinline__ void exec_misc(const TravScene sc, SavedRays &stk, DRAW &&draw) {
+    template <int LEVEL, int NEST, typename DS>
+    __device__ __forceinline__ void exec_misc(const TravScene sc, SavedRays &stk, DS &draw) {
         bool hit = false;
         const uint32_t kind = h.x & 0xffu;
         if (kind == RTGPU_OP_POP) {
@@ -467,7 +493,7 @@ struct Traversal {
             i += 2;
             break;
         case RTGPU_OP_MEDIUM:
-            if constexpr (MAIN) { /* ConstantMedium::hit, constantmedium.rs:49-83 */
+            if constexpr (LEVEL < NEST) { /* ConstantMedium::hit, constantmedium.rs:49-83 */
                 double t1 = CUDART_INF, t2 = CUDART_INF;
                 bool h1, h2 = false;
                 const double a = length_sqr(d);
@@ -481,11 +507,13 @@ struct Traversal {
                     if (h1) h2 = hit_sphere(o, d, a, c0, bp[3], t1 + 0.0001, t2);
                 } else {
                     const double tm = ray.tm();
-                    Closest r1 = closest_hit_boundary(sc, i + 2, h.y, o, d, tm, -CUDART_INF, CUDART_INF);
+                    BoundaryHit r1 = closest_hit_boundary<LEVEL + 1, NEST>(sc, i + 2, h.y, o, d, tm, -CUDART_INF, CUDART_INF, draw.stream());
+                    draw.pos = r1.face;
                     h1 = r1.op != RT_NO_HIT;
                     t1 = r1.t;
                     if (h1) {
-                        Closest r2 = closest_hit_boundary(sc, i + 2, h.y, o, d, tm, t1 + 0.0001, CUDART_INF);
+                        BoundaryHit r2 = closest_hit_boundary<LEVEL + 1, NEST>(sc, i + 2, h.y, o, d, tm, t1 + 0.0001, CUDART_INF, draw.stream());
+                        draw.pos = r2.face;
                         h2 = r2.op != RT_NO_HIT;
                         t2 = r2.t;
                     }
@@ -531,30 +559,41 @@ struct Traversal {
         fetch_op(sc);
     }
     /* one op, whatever it is (single-ray loops) */
-    template <bool MAIN, typename DRAW>
-    __device__ __forceinline__ void step(const TravScene sc, SavedRays &stk, DRAW &&draw) {
+    template <int LEVEL, int NEST, typename DS>
+    __device__ __forceinline__ void step(const TravScene sc, SavedRays &stk, DS &draw) {
         switch (phase()) {
         case PH_NODE: exec_node(sc); break;
         case PH_EXACT: exec_node_exact(sc); break;
         case PH_SPHERE: exec_sphere(sc); break;
         case PH_BOX: exec_box(sc); break;
         case PH_TRI: exec_tri(sc); break;
-        default: exec_misc<MAIN>(sc, stk, draw); break;
+        default: exec_misc<LEVEL, NEST>(sc, stk, draw); break;
         }
     }
 };
 
 /* boundary walk of a medium whose boundary is not a single sphere: rare, kept out of line */
-__device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm,
-                                                     double tmin, double tmax) {
+template <int LEVEL, int NEST>
+__device__ __noinline__ BoundaryHit closest_hit_boundary(const TravScene sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm,
+                                                         double tmin, double tmax, StreamDraw ds) {
     Traversal<RayRegs> tr;
     SavedRays stk;
     TravScene sub = sc;
     sub.end = end;
     tr.start(sub, begin, o, d, tm, tmin, tmax);
-    while (!tr.done(sub)) tr.step<false>(sub, stk, []() { return 0.; });
-    return tr.best;
+    while (!tr.done(sub)) tr.template step<LEVEL, NEST>(sub, stk, ds);
+    BoundaryHit r = tr.best;
+    r.face = ds.pos;
+    return r;
 }
+/* the stream of the ray a lane of k_extend / k_trace_extend owns */
+template <typename IO>
+struct LaneDraw {
+    const IO &io; /* never leaves the (inlined) warp loop: the boundary walk gets stream(), a value */
+    uint32_t a, b, pos;
+    __device__ __forceinline__ double operator()() { return io.draw(a, b, pos); }
+    __device__ __forceinline__ StreamDraw stream() const { return io.stream(a, b, pos); }
+};
 
 #ifndef RT_EXTEND_REFILL
 #define RT_EXTEND_REFILL 16 /* refill when at least this many lanes of the warp are idle (a refill stalls the whole warp on the
@@ -590,7 +629,7 @@ __device__ __noinline__ Closest closest_hit_boundary(const TravScene sc, uint32_
  *  shared-memory queues, and a full pool of rays in shared memory with one queue per phase: both bit-exact, both
  *  slower (1 095 and 1 606 against 2 235 Mrays/s): the queue upkeep costs more instructions and L1/shared-memory
  *  data-pipe cycles than the fuller warps save.  They are in the history of this file, not in the tree.) */
-template <typename IO>
+template <int NEST, typename IO>
 __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_units, uint32_t n, uint32_t *fetch, IO &io) {
     const uint32_t lane = threadIdx.x & 31u;
     Traversal<RayRegsT<IO::kConstTmin>> tr;
@@ -675,7 +714,12 @@ __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_
             case PH_SPHERE: tr.exec_sphere(ts); break;
             case PH_BOX: tr.exec_box(ts); break;
             case PH_TRI: tr.exec_tri(ts); break;
-            default: tr.template exec_misc<true>(ts, stk, [&]() { return io.draw(rng_a, rng_b, rng_pos); }); break;
+            default: {
+                LaneDraw<IO> draw{io, rng_a, rng_b, rng_pos};
+                tr.template exec_misc<0, NEST>(ts, stk, draw);
+                rng_pos = draw.pos;
+                break;
+            }
             }
             if (tr.done(ts)) {
                 io.store(cur, tr.best, rng_pos);

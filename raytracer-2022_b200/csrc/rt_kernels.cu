@@ -251,6 +251,10 @@ struct QueueIO {
     __device__ __forceinline__ void prefetch(uint32_t idx) {
         if (!perm) asm volatile("prefetch.global.L2 [%0];" ::"l"(q.ray + idx));
     }
+    __device__ __forceinline__ StreamDraw stream(uint32_t a, uint32_t, uint32_t pos) const { /* the same stream, resolved */
+        uint32_t pixel = wp.first_pixel + a % wp.npix_wave, sample = wp.sample_begin + a / wp.npix_wave;
+        return StreamDraw{wp.seed, pixel, sample, RT_DOMAIN_PATH, pos};
+    }
     __device__ __forceinline__ double draw(uint32_t a, uint32_t, uint32_t &pos) const { /* the path's stream resumes at slot `pos` */
         rt_rng rng;
         path_rng(rng, wp, a, pos);
@@ -271,6 +275,8 @@ struct QueueIO {
 #endif
     }
 };
+/* NEST: see closest_hit_boundary (rt_device.cuh) -- 1 for every scene without a medium inside a medium's boundary */
+template <int NEST>
 __global__ void __launch_bounds__(kThreads, RT_EXTEND_MIN_BLOCKS) k_extend(DScene sc, PathQueue q, HitBuf hb, WaveCtl *ctl, int cur,
                                                                            WaveParams wp, const uint32_t *perm, uint32_t n_perm) {
     QueueIO io;
@@ -279,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, RT_EXTEND_MIN_BLOCKS) k_extend(DScen
     io.wp = wp;
     io.perm = perm;
     io.n_perm = perm ? n_perm : 0u;
-    extend_warp_loop(trav_of(sc), sc.n_units, ctl->count[cur], &ctl->fetch, io);
+    extend_warp_loop<NEST>(trav_of(sc), sc.n_units, ctl->count[cur], &ctl->fetch, io);
 }
 
 /* ---- ray reordering between bounces ---------------------------------------------------------------
@@ -627,6 +633,7 @@ __global__ void k_finish(PathSink sk, float *accum, uint32_t npix, int add) {
  * paths in ONE launch: a thread takes a queue entry and runs its path to the end -- the single-ray walk of the traversal program
  * (the same Traversal::step the medium boundaries use) and the same shade_segment<class>() as the class kernels, so every path
  * gets bit for bit what the iterations would have given it. */
+template <int NEST>
 __global__ void __launch_bounds__(kThreads) k_tail(DScene sc, PathQueue q, WaveCtl *ctl, int cur, PathSink sk, WaveParams wp) {
     const uint32_t n = ctl->count[cur];
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -647,15 +654,9 @@ __global__ void __launch_bounds__(kThreads) k_tail(DScene sc, PathQueue q, WaveC
             Traversal<RayRegs> tr;
             SavedRays stk;
             tr.start(ts, 0, r.o, r.d, r.tm, 0.001, RT_F64_MAX);
-            while (!tr.done(ts)) {
-                tr.step<true>(ts, stk, [&]() {
-                    rt_rng g;
-                    path_rng(g, wp, pid, pos);
-                    double u = g.gen();
-                    pos = g.pos;
-                    return u;
-                });
-            }
+            StreamDraw draw{wp.seed, wp.first_pixel + pid % wp.npix_wave, wp.sample_begin + pid / wp.npix_wave, RT_DOMAIN_PATH, pos};
+            while (!tr.done(ts)) tr.step<0, NEST>(ts, stk, draw);
+            pos = draw.pos;
             ++my_rays;
             const uint32_t hop = tr.best.op == RT_NO_HIT ? RT_NO_HIT : (tr.best.op | (tr.best.face << 29));
             const uint32_t cls = tr.best.op == RT_NO_HIT ? 0u : tr.best.cls;
@@ -724,6 +725,9 @@ struct BatchIO {
     }
     __device__ __forceinline__ int refill_at() const { return RT_EXTEND_REFILL; }
     __device__ __forceinline__ void prefetch(uint32_t idx) { asm volatile("prefetch.global.L2 [%0];" ::"l"(rays + idx)); }
+    __device__ __forceinline__ StreamDraw stream(uint32_t a, uint32_t b, uint32_t pos) const {
+        return StreamDraw{((uint64_t)b << 32) | (uint64_t)a, 0u, 0u, RT_DOMAIN_BATCH, pos};
+    }
     __device__ __forceinline__ double draw(uint32_t a, uint32_t b, uint32_t &pos) const {
         rt_rng rng;
         rng.init(((uint64_t)b << 32) | (uint64_t)a, 0, 0, RT_DOMAIN_BATCH, pos);
@@ -737,6 +741,7 @@ struct BatchIO {
         rng_pos[cur] = pos;
     }
 };
+template <int NEST>
 __global__ void __launch_bounds__(kThreads, RT_EXTEND_MIN_BLOCKS) k_trace_extend(DScene sc, const rtgpu_ray *rays, const uint64_t *keys, double *t,
                                                                    uint32_t *op, uint32_t *rng_pos, uint32_t n, uint32_t *fetch) {
     BatchIO io;
@@ -745,7 +750,7 @@ __global__ void __launch_bounds__(kThreads, RT_EXTEND_MIN_BLOCKS) k_trace_extend
     io.t = t;
     io.op = op;
     io.rng_pos = rng_pos;
-    extend_warp_loop(trav_of(sc), sc.n_units, n, fetch, io);
+    extend_warp_loop<NEST>(trav_of(sc), sc.n_units, n, fetch, io);
 }
 __global__ void __launch_bounds__(kThreads) k_trace_record(DScene sc, const rtgpu_ray *rays, const double *t, const uint32_t *op,
                                                            const uint32_t *rng_pos, rtgpu_hit *out, uint32_t n) {
@@ -878,6 +883,7 @@ struct rtgpu_scene : WaveRes {
     DScene d;
     std::vector<void *> allocs;
     bool class_present[8] = {true, false, false, false, false, false, false, false};
+    int medium_nesting = 0; /* deepest ConstantMedium-inside-a-boundary nesting of the program: picks the NEST of the walk kernels */
     int run_ahead = kRunAheadDefault; /* RTGPU_RUN_AHEAD: iterations the host may be ahead of the device (1 .. 32) */
     uint32_t tail_max = 1u << 16; /* RTGPU_TAIL_MAX: at most this many live paths are finished by k_tail in one launch (0 = never) */
     int sort_mode = 1;          /* RTGPU_SORT_RAYS=0: never reorder rays between bounces */
@@ -909,7 +915,8 @@ struct SceneArena {
     rtgpu_status commit(rtgpu_scene *s);
 };
 
-rtgpu_status validate(const rtgpu_scene_desc *d) {
+rtgpu_status validate(const rtgpu_scene_desc *d, int *medium_nesting) {
+    *medium_nesting = 0;
     auto bad = [](const char *m) {
         g_err = m;
         return RTGPU_ERR_INVALID_SCENE;
@@ -924,15 +931,23 @@ rtgpu_status validate(const rtgpu_scene_desc *d) {
     for (uint32_t i = 0; i < d->n_chain; ++i)
         if (d->chain[i] >= d->n_xforms) return bad("chain entry outside the xform array");
     int push = 0;
+    std::vector<uint32_t> medium_ends; /* skip targets of the ConstantMedium ops whose boundary the scan is inside of */
     for (uint32_t i = 0; i < d->n_ops;) {
+        while (!medium_ends.empty() && i >= medium_ends.back()) medium_ends.pop_back();
         const rtgpu_op &op = d->ops[i];
         uint32_t kind = op.kind_ctx & 0xff, ctx = op.kind_ctx >> 8;
         uint32_t width = (kind == RTGPU_OP_MSPHERE || kind == RTGPU_OP_TRI) ? 2 : 1;
         if (i + width > d->n_ops) return bad("two-slot op at the end of the program");
         switch (kind) {
         case RTGPU_OP_NODE:
+            if (op.skip <= i || op.skip > d->n_ops) return bad("skip index out of range");
+            break;
         case RTGPU_OP_MEDIUM:
             if (op.skip <= i || op.skip > d->n_ops) return bad("skip index out of range");
+            if (!medium_ends.empty() && op.skip > medium_ends.back()) return bad("ConstantMedium boundaries overlap");
+            medium_ends.push_back(op.skip);
+            if (medium_ends.size() > RT_MAX_MEDIUM_NESTING) return bad("ConstantMedium boundaries nested deeper than RT_MAX_MEDIUM_NESTING");
+            if ((int)medium_ends.size() > *medium_nesting) *medium_nesting = (int)medium_ends.size();
             break;
         case RTGPU_OP_PUSH:
             if ((uint64_t)op.a + op.b > d->n_chain) return bad("PUSH chain out of range");
@@ -1196,7 +1211,8 @@ rtgpu_status run_paths(rtgpu_scene *s, const WaveParams &wp, const PathSink &sk,
         PathQueue &qin = s->q[cur], &qout = s->q[cur ^ 1];
         if ((st = mark()) != RTGPU_OK) return st;
         if (allow_tail && gen_done && alive_ub <= s->tail_max && it > 0) { /* the few paths that are left run to their end in one launch */
-            k_tail<<<blocks, kThreads, 0, stream>>>(s->d, qin, s->ctl, cur, sk, wp);
+            if (s->medium_nesting > 1) k_tail<2><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->ctl, cur, sk, wp);
+            else k_tail<1><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->ctl, cur, sk, wp);
             k_tail_done<<<1, 1, 0, stream>>>(s->ctl, cur);
             CK(cudaGetLastError());
             if (wt) wt->launches += 2;
@@ -1222,7 +1238,8 @@ rtgpu_status run_paths(rtgpu_scene *s, const WaveParams &wp, const PathSink &sk,
         }
         phase_of_event.push_back(0);
         if ((st = mark()) != RTGPU_OK) return st;
-        k_extend<<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->ctl, cur, wp, perm, bound);
+        if (s->medium_nesting > 1) k_extend<2><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->ctl, cur, wp, perm, bound);
+        else k_extend<1><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->ctl, cur, wp, perm, bound);
         CK(cudaGetLastError()); /* a failed extend launch must not let the shade kernels read stale hits */
         phase_of_event.push_back(1);
         if ((st = mark()) != RTGPU_OK) return st;
@@ -1342,7 +1359,8 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
         return RTGPU_ERR_INVALID_ARG;
     }
     *out = nullptr;
-    rtgpu_status st = validate(desc);
+    int medium_nesting = 0;
+    rtgpu_status st = validate(desc, &medium_nesting);
     if (st != RTGPU_OK) return st;
     if (device >= 0) CK(cudaSetDevice(device));
     int cur = 0;
@@ -1350,6 +1368,7 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
     rtgpu_scene *s = new (std::nothrow) rtgpu_scene();
     if (!s) return RTGPU_ERR_OOM;
     s->device = cur;
+    s->medium_nesting = medium_nesting;
     if (cudaDeviceGetAttribute(&s->n_sm, cudaDevAttrMultiProcessorCount, cur) != cudaSuccess || s->n_sm < 1) {
         cudaGetLastError();
         s->n_sm = 148;
@@ -1593,7 +1612,10 @@ rtgpu_status rtgpu_trace_batch(rtgpu_scene *s, const rtgpu_ray *rays, int64_t n,
         CK(cudaEventCreate(&e0));
         CK(cudaEventCreate(&e1));
         CK(cudaEventRecord(e0, 0));
-        k_trace_extend<<<grid_blocks(s), kThreads>>>(s->d, d_rays, d_keys, d_t, d_u32, d_u32 + n, (uint32_t)n, d_u32 + 2 * n);
+        if (s->medium_nesting > 1)
+            k_trace_extend<2><<<grid_blocks(s), kThreads>>>(s->d, d_rays, d_keys, d_t, d_u32, d_u32 + n, (uint32_t)n, d_u32 + 2 * n);
+        else
+            k_trace_extend<1><<<grid_blocks(s), kThreads>>>(s->d, d_rays, d_keys, d_t, d_u32, d_u32 + n, (uint32_t)n, d_u32 + 2 * n);
         CK(cudaEventRecord(e1, 0));
         k_trace_record<<<grid_blocks(s), kThreads>>>(s->d, d_rays, d_t, d_u32, d_u32 + n, d_out, (uint32_t)n);
         CK(cudaGetLastError());

@@ -99,6 +99,7 @@ struct Lowerer {
         return (uint32_t)o.mat;
     }
 
+    int medium_depth = 0; // ConstantMedium boundaries the op being emitted is inside of
     void emit(int32_t id, bool in_boundary) {
         if (++depth > 100000) throw Error{"lower: object graph too deep (cycle?)"};
         const rt_object &o = obj(id);
@@ -149,10 +150,14 @@ struct Lowerer {
             break;
         }
         case RT_OBJ_MEDIUM: {
-            if (in_boundary) throw Error{"lower: a ConstantMedium inside a ConstantMedium boundary is not supported"};
+            // upstream's ConstantMedium<H> takes any Hittable as its boundary, another ConstantMedium included
+            // (constantmedium.rs:14-43); the device walks two levels (RT_MAX_MEDIUM_NESTING)
+            if (medium_depth >= 2) throw Error{"lower: ConstantMedium boundaries nested deeper than 2 are not supported"};
             uint32_t i = push_op(RTGPU_OP_MEDIUM, current_ctx(), mat_of(o), (uint32_t)id);
             out.ops[i].d[0] = -1. / p[0]; // neg_inv_density, constantmedium.rs:29,39
+            ++medium_depth;
             emit(o.c0, true);
+            --medium_depth;
             out.ops[i].skip = (uint32_t)out.ops.size();
             break;
         }

@@ -105,6 +105,27 @@ def test_lowering_program_invariants():
     assert full.desc.n_ops >= lw.desc.n_ops
 
 
+def test_media_nest_two_deep_and_no_deeper():
+    """ConstantMedium<H> over a boundary that holds another ConstantMedium (constantmedium.rs:14-43 is generic) lowers to
+    MEDIUM ops nested two deep; three deep is refused by the lowering (RT_MAX_MEDIUM_NESTING), never mis-rendered."""
+    def world(s, levels):
+        m = s.constant_medium(s.sphere((0, 0, 0), 1.0, s.dielectric(1.5)), 0.8, (1, 0, 0))
+        for _ in range(levels - 1):
+            m = s.constant_medium(s.bvh_node([m, s.sphere((0.2, 0, 0), 1.5, s.dielectric(1.5))]), 0.5, (0, 1, 0))
+        return m
+
+    s = rt.Scene(seed=1)
+    s.set_world(world(s, 2))
+    ops = s.lower().ops()
+    kinds = ops["kind_ctx"] & 0xFF
+    med = [i for i in range(len(ops)) if kinds[i] == D.OP_MEDIUM]
+    assert len(med) >= 2 and any(a < b < ops["skip"][a] for a in med for b in med)  # one boundary range inside the other
+    s3 = rt.Scene(seed=1)
+    s3.set_world(world(s3, 3))
+    with pytest.raises(rt.RtError, match="nested deeper"):
+        s3.lower()
+
+
 def test_scene_errors_mirror_reference_panics():
     s = rt.Scene(seed=1)
     with pytest.raises(rt.RtError, match="empty"):
