@@ -77,6 +77,21 @@ struct DScene {
     double background[3];
 };
 
+/* What the out-of-line helpers need of the scene, BY VALUE: a `const DScene &` of the kernel's parameter block makes the compiler
+ * copy the whole block (camera included) into local memory just to have an address to pass. */
+struct TexTables {
+    const rtgpu_texture *texs;
+    const rtgpu_perlin *perlins;
+    const rtgpu_image *images;
+    const uint8_t *texels;
+};
+__device__ __forceinline__ TexTables tex_of(const DScene &sc) { return TexTables{sc.texs, sc.perlins, sc.images, sc.texels}; }
+struct LightTable {
+    const rtgpu_light *lights;
+    uint32_t n_lights, n_light_roots;
+};
+__device__ __forceinline__ LightTable lights_of(const DScene &sc) { return LightTable{sc.lights, sc.n_lights, sc.n_light_roots}; }
+
 /* ---- 128-bit loads of an op ------------------------------------------------------------- */
 __device__ __forceinline__ const uint4 *unit_ptr(const uint4 *prog, uint32_t unit) { return prog + 2 * (size_t)unit; }
 __device__ __forceinline__ uint4 load_op_header(const uint4 *op) { return __ldg(op); }
@@ -299,8 +314,11 @@ struct StreamDraw {
 /* NEST = how many levels of ConstantMedium boundaries the instantiation walks.  Kernels exist for NEST 1 and 2: the mere presence
  * of the LEVEL 2 walk behind the out-of-line call makes ptxas keep the warp loop's state in local memory (k_extend 2x slower,
  * measured), so scenes without a medium inside a medium's boundary -- all of the reference's -- run the NEST 1 kernels. */
+#ifndef RT_BOUNDARY_CALL
+#define RT_BOUNDARY_CALL __noinline__
+#endif
 template <int LEVEL, int NEST>
-__device__ __noinline__ BoundaryHit closest_hit_boundary(const TravScene sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm,
+__device__ RT_BOUNDARY_CALL BoundaryHit closest_hit_boundary(const TravScene sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm,
                                                          double tmin, double tmax, StreamDraw ds);
 
 /* phases of the warp scheduler: ops whose code is the same run together */
@@ -493,7 +511,7 @@ struct Traversal {
             i += 2;
             break;
         case RTGPU_OP_MEDIUM:
-            if constexpr (LEVEL < NEST) { /* ConstantMedium::hit, constantmedium.rs:49-83 */
+            if constexpr (LEVEL < NEST || LEVEL == 0) { /* ConstantMedium::hit, constantmedium.rs:49-83 */
                 double t1 = CUDART_INF, t2 = CUDART_INF;
                 bool h1, h2 = false;
                 const double a = length_sqr(d);
@@ -505,7 +523,7 @@ struct Traversal {
                     V3 c0 = v3(bp[0], bp[1], bp[2]);
                     h1 = hit_sphere(o, d, a, c0, bp[3], -CUDART_INF, t1);
                     if (h1) h2 = hit_sphere(o, d, a, c0, bp[3], t1 + 0.0001, t2);
-                } else {
+                } else if constexpr (LEVEL < NEST) {
                     const double tm = ray.tm();
                     BoundaryHit r1 = closest_hit_boundary<LEVEL + 1, NEST>(sc, i + 2, h.y, o, d, tm, -CUDART_INF, CUDART_INF, draw.stream());
                     draw.pos = r1.face;
@@ -517,6 +535,8 @@ struct Traversal {
                         h2 = r2.op != RT_NO_HIT;
                         t2 = r2.t;
                     }
+                } else {
+                    h1 = false; /* NEST 0: rtgpu_scene_create found every boundary to be one Sphere */
                 }
                 if (h1 && h2) {
                     t1 = fmax(t1, tmin);
@@ -574,7 +594,7 @@ struct Traversal {
 
 /* boundary walk of a medium whose boundary is not a single sphere: rare, kept out of line */
 template <int LEVEL, int NEST>
-__device__ __noinline__ BoundaryHit closest_hit_boundary(const TravScene sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm,
+__device__ RT_BOUNDARY_CALL BoundaryHit closest_hit_boundary(const TravScene sc, uint32_t begin, uint32_t end, V3 o, V3 d, double tm,
                                                          double tmin, double tmax, StreamDraw ds) {
     Traversal<RayRegs> tr;
     SavedRays stk;
@@ -762,8 +782,12 @@ __device__ __forceinline__ void rect_record(HitRec &rec, V3 o, V3 d, double a0, 
 }
 
 /* WANT_UV = false skips the sphere's acos/atan2 (only an ImageTexture reads u, v of a sphere) */
+#ifndef RT_RECORD_CALL
+#define RT_RECORD_CALL __forceinline__ /* out of line, `rec`, the ray and the kernel's whole parameter block go through local memory: the
+                                          shade stage of C3 was 34.5 ms with the call, 30.9 inlined */
+#endif
 template <bool WANT_UV>
-__device__ __noinline__ void make_record(const DScene &sc, const Ray &wr, double t, uint32_t opi, uint32_t face, HitRec &rec) {
+__device__ RT_RECORD_CALL void make_record(const DScene &sc, const Ray &wr, double t, uint32_t opi, uint32_t face, HitRec &rec) {
     const uint4 *op = unit_ptr(sc.prog, opi);
     uint4 h = load_op_header(op);
     uint32_t kind = h.x & 0xffu;
@@ -876,7 +900,11 @@ __device__ __noinline__ void make_record(const DScene &sc, const Ray &wr, double
 /* f64 sin/cos expand to ~200 instructions each (plus the Payne-Hanek slow path); one out-of-line copy keeps
  * k_shade small enough for the instruction cache (ncu: `no_instruction` was its top stall). */
 __device__ __noinline__ double rt_sin(double x) { return sin(x); }
-__device__ __noinline__ void rt_sincos(double x, double *s, double *c) { sincos(x, s, c); }
+__device__ __noinline__ double2 rt_sincos(double x) { /* (sin, cos), returned in registers */
+    double2 r;
+    sincos(x, &r.x, &r.y);
+    return r;
+}
 
 /* ---- textures (texture/mod.rs, texture/perlin.rs) ------------------------------------------ */
 __device__ __forceinline__ int32_t floor_i32(double f) { /* `as i32`: saturating, NaN -> 0 */
@@ -924,7 +952,7 @@ __device__ double perlin_turb(const rtgpu_perlin &t, V3 p, int depth) { /* perli
 #define RT_TEXMASK_SIMPLE 0x3 /* SolidColor, CheckerTexture over SolidColors */
 #define RT_TEXMASK_ALL 0xf
 template <int TEXMASK>
-__device__ __noinline__ V3 texture_value(const DScene &sc, uint32_t id, double u, double v, V3 p) {
+__device__ __noinline__ V3 texture_value(const TexTables sc, uint32_t id, double u, double v, V3 p) {
     for (int depth = 0; depth < 16; ++depth) {
         const rtgpu_texture &t = sc.texs[id];
         uint32_t kind = t.kind;
@@ -987,8 +1015,8 @@ __device__ __forceinline__ V3 random_cosine_direction(rt_rng &rng) { /* pdf.rs:1
     double r2 = rng.gen();
     double z = sqrt(1. - r2);
     double phi = 2. * RT_PI * r1;
-    double sn, cs;
-    rt_sincos(phi, &sn, &cs);
+    const double2 sc2 = rt_sincos(phi);
+    const double sn = sc2.x, cs = sc2.y;
     double x = cs * sqrt(r2);
     double y = sn * sqrt(r2);
     return v3(x, y, z);
@@ -998,8 +1026,8 @@ __device__ __forceinline__ V3 random_to_sphere(rt_rng &rng, double radius, doubl
     double r2 = rng.gen();
     double z = 1. + r2 * (sqrt(1. - radius * radius / dis_sqr) - 1.);
     double phi = 2. * RT_PI * r1;
-    double sn, cs;
-    rt_sincos(phi, &sn, &cs);
+    const double2 sc2 = rt_sincos(phi);
+    const double sn = sc2.x, cs = sc2.y;
     double x = cs * sqrt(1. - z * z);
     double y = sn * sqrt(1. - z * z);
     return v3(x, y, z);
@@ -1066,7 +1094,12 @@ __device__ __forceinline__ double light_pdf_value(const rtgpu_light &l, V3 o, V3
 /* HittableList::pdf_value (hittable/mod.rs:121-128) over `lights`: the mean of the members' values, a member that is a
  * HittableList contributing the mean over ITS members.  Sums run in member order, as upstream; the recursion is unrolled
  * over an explicit stack (RTGPU_MAX_LIGHT_NESTING levels, checked when the scene is created). */
-__device__ __noinline__ double lights_pdf_value(const DScene &sc, V3 o, V3 v) {
+__device__ __noinline__ double lights_pdf_value(const LightTable sc, V3 o, V3 v) {
+    if (sc.n_lights == sc.n_light_roots) { /* no HittableList inside `lights` (every reference scene): the same sums without the stack */
+        double sum = 0.;
+        for (uint32_t k = 0; k < sc.n_light_roots; ++k) sum += light_pdf_value(sc.lights[k], o, v);
+        return sum / (double)sc.n_light_roots;
+    }
     uint32_t at[RTGPU_MAX_LIGHT_NESTING + 1], end[RTGPU_MAX_LIGHT_NESTING + 1];
     double sum[RTGPU_MAX_LIGHT_NESTING + 1], len[RTGPU_MAX_LIGHT_NESTING + 1];
     int sp = 0;
@@ -1096,7 +1129,10 @@ __device__ __noinline__ double lights_pdf_value(const DScene &sc, V3 o, V3 v) {
 }
 /* HittableList::random (hittable/mod.rs:129-132): uniform pick of a member (one draw), then that member's random();
  * a member that is a HittableList picks again */
-__device__ __noinline__ V3 lights_random(const DScene &sc, V3 o, rt_rng &rng) {
+#ifndef RT_LIGHTS_RANDOM_CALL
+#define RT_LIGHTS_RANDOM_CALL __forceinline__ /* out of line, `rng` is passed by address and lives in local memory for the whole kernel */
+#endif
+__device__ RT_LIGHTS_RANDOM_CALL V3 lights_random(const LightTable sc, V3 o, rt_rng &rng) {
     uint32_t target = rng.gen_index(sc.n_light_roots);
     const rtgpu_light *lp = sc.lights + target;
     for (int depth = 0; lp->kind == RTGPU_LIGHT_LIST && depth < RTGPU_MAX_LIGHT_NESTING; ++depth)

@@ -59,7 +59,8 @@ constexpr int kThreads = RT_THREADS;
 #define RT_SHADE_THREADS 64
 #endif
 #ifndef RT_SHADE_BLOCKS_PER_SM
-#define RT_SHADE_BLOCKS_PER_SM 8 /* 16 warps/SM: measured best (5 % over 32 warps/SM) */
+#define RT_SHADE_BLOCKS_PER_SM 12 /* 24 warps/SM at <= 80 registers (RT_SHADE_MIN_BLOCKS).  A/B on C3, ms in the shade stage:
+                                     8 blocks/SM (<= 128 registers) 30.1, 10 (<= 96) 28.8, 12 (<= 80) 27.8 */
 #endif
 constexpr int kShadeThreads = RT_SHADE_THREADS;
 
@@ -223,7 +224,11 @@ __global__ void k_pad_keys(const WaveCtl *ctl, uint32_t *keys, uint32_t pad_to) 
 }
 /* world.hit(r, 0.001, f64::MAX), main.rs:243 -- persistent warps, see extend_warp_loop */
 #ifndef RT_EXTEND_MIN_BLOCKS
-#define RT_EXTEND_MIN_BLOCKS 4
+#define RT_EXTEND_MIN_BLOCKS 4 /* NEST >= 1: the out-of-line boundary walk costs the warp loop ~20 registers of spills even at 128 */
+#endif
+#ifndef RT_EXTEND_MIN_BLOCKS0
+#define RT_EXTEND_MIN_BLOCKS0 7 /* NEST 0 (no call in the loop): 72 registers, 28 warps/SM -- A/B on C3 (64 spp), ms in k_extend:
+                                  4: 78.0, 5: 68.9, 6: 68.5, 7: 67.4, 8: 68.8; the other scenes agree (7 best on C1, C2, wwscene) */
 #endif
 struct QueueIO {
     static constexpr bool kConstTmin = true; /* world.hit(r, 0.001, f64::MAX), main.rs:243 */
@@ -277,7 +282,7 @@ struct QueueIO {
 };
 /* NEST: see closest_hit_boundary (rt_device.cuh) -- 1 for every scene without a medium inside a medium's boundary */
 template <int NEST>
-__global__ void __launch_bounds__(kThreads, RT_EXTEND_MIN_BLOCKS) k_extend(DScene sc, PathQueue q, HitBuf hb, WaveCtl *ctl, int cur,
+__global__ void __launch_bounds__(kThreads, NEST == 0 ? RT_EXTEND_MIN_BLOCKS0 : RT_EXTEND_MIN_BLOCKS) k_extend(DScene sc, PathQueue q, HitBuf hb, WaveCtl *ctl, int cur,
                                                                            WaveParams wp, const uint32_t *perm, uint32_t n_perm) {
     QueueIO io;
     io.q = q;
@@ -412,23 +417,41 @@ __global__ void __launch_bounds__(kThreads) k_regen(DScene sc, PathQueue q, cons
  *   class 3  Metal            class 4  Dielectric                class 5  Isotropic (ConstantMedium) */
 constexpr int kClasses = 6;
 
-__global__ void __launch_bounds__(256) k_classify(HitBuf hb, WaveCtl *ctl, int cur, uint32_t *class_idx, uint32_t cap) {
-    uint32_t n = ctl->count[cur];
-    uint32_t *class_count = ctl->class_count;
-    uint32_t stride = gridDim.x * blockDim.x;
-    uint32_t lane = threadIdx.x & 31u;
-    for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < n; i0 += stride) {
-        uint32_t i = i0 + lane;
-        uint32_t cls = 0xffu;
-        if (i < n) cls = hb.rec[i].rng >> 29; /* written by k_extend: 0 for a miss, else the class of the material that was hit */
-        uint32_t peers = __match_any_sync(0xffffffffu, cls);
-        if (cls != 0xffu) {
-            int leader = __ffs(peers) - 1;
-            uint32_t base = 0;
-            if ((int)lane == leader) base = atomicAdd(class_count + cls, (uint32_t)__popc(peers));
-            base = __shfl_sync(peers, base, leader);
-            class_idx[(size_t)cls * cap + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = i;
+/* A block bins a tile of 256 x 8 hits: warp-aggregated shared-memory counters give every hit its rank inside the tile, then ONE global
+ * atomic per class and tile reserves the tile's ranges of the class lists.  (One global atomic per warp and class -- 1.2 M of them on
+ * six addresses per iteration -- kept this kernel at 0.3 ms for 0.3 GB of traffic: same-address atomics retire ~1 per L2 clock.) */
+constexpr int kClassifyThreads = 256, kClassifyPerThread = 8;
+__global__ void __launch_bounds__(kClassifyThreads) k_classify(HitBuf hb, WaveCtl *ctl, int cur, uint32_t *class_idx, uint32_t cap) {
+    __shared__ uint32_t s_cnt[8], s_base[8];
+    const uint32_t n = ctl->count[cur];
+    const uint32_t lane = threadIdx.x & 31u;
+    constexpr uint32_t kTile = kClassifyThreads * kClassifyPerThread;
+    for (uint32_t tile0 = blockIdx.x * kTile; tile0 < n; tile0 += gridDim.x * kTile) {
+        if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t cls[kClassifyPerThread], rank[kClassifyPerThread];
+#pragma unroll
+        for (int k = 0; k < kClassifyPerThread; ++k) {
+            const uint32_t i = tile0 + k * kClassifyThreads + threadIdx.x;
+            cls[k] = i < n ? hb.rec[i].rng >> 29 : 0xffu; /* written by k_extend: 0 for a miss, else the class of the material that was hit */
         }
+#pragma unroll
+        for (int k = 0; k < kClassifyPerThread; ++k) {
+            const uint32_t peers = __match_any_sync(0xffffffffu, cls[k]);
+            rank[k] = 0;
+            if (cls[k] != 0xffu) {
+                const int leader = __ffs(peers) - 1;
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(&s_cnt[cls[k]], (uint32_t)__popc(peers));
+                rank[k] = __shfl_sync(peers, base, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 8) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(ctl->class_count + threadIdx.x, s_cnt[threadIdx.x]) : 0u;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kClassifyPerThread; ++k)
+            if (cls[k] != 0xffu) class_idx[(size_t)cls[k] * cap + s_base[cls[k]] + rank[k]] = tile0 + k * kClassifyThreads + threadIdx.x;
     }
 }
 
@@ -446,7 +469,7 @@ __device__ __forceinline__ bool shade_segment(const DScene &sc, const Ray &r, do
         HitRec rec;
         make_record<true>(sc, r, t, hop & 0x1fffffffu, hop >> 29, rec);
         const rtgpu_material &m = sc.mats[rec.mat];
-        V3 e = rec.front ? texture_value<RT_TEXMASK_ALL>(sc, m.tex, rec.u, rec.v, rec.p) : v3(0., 0., 0.);
+        V3 e = rec.front ? texture_value<RT_TEXMASK_ALL>(tex_of(sc), m.tex, rec.u, rec.v, rec.p) : v3(0., 0., 0.);
         contrib = beta * e;
         return false;
     } else {
@@ -478,10 +501,10 @@ __device__ __forceinline__ bool shade_segment(const DScene &sc, const Ray &r, do
             next.o = rec.p;
             next.d = random_in_unit_sphere(rng);
             next.tm = r.tm;
-            beta = beta * texture_value<RT_TEXMASK_ALL>(sc, m.tex, rec.u, rec.v, rec.p);
+            beta = beta * texture_value<RT_TEXMASK_ALL>(tex_of(sc), m.tex, rec.u, rec.v, rec.p);
             return true;
         } else { /* Lambertian + MixturePdf(HittablePdf(lights), CosPdf), main.rs:263-271 */
-            V3 attenuation = texture_value<(CLS == 1 ? RT_TEXMASK_SIMPLE : RT_TEXMASK_ALL)>(sc, m.tex, rec.u, rec.v, rec.p);
+            V3 attenuation = texture_value<(CLS == 1 ? RT_TEXMASK_SIMPLE : RT_TEXMASK_ALL)>(tex_of(sc), m.tex, rec.u, rec.v, rec.p);
             Onb uvw = onb_from_w(rec.n); /* CosPdf::new(rec.normal), pdf.rs:35-39 */
             V3 direction;
             double pdf_val;
@@ -492,12 +515,12 @@ __device__ __forceinline__ bool shade_segment(const DScene &sc, const Ray &r, do
                 pdf_val = c <= 0. ? 0. : c / RT_PI;
             } else {
                 if (rng.gen_range(0.0, 1.0) < 0.5) /* MixturePdf::generate, pdf.rs:95-101 */
-                    direction = lights_random(sc, rec.p, rng);
+                    direction = lights_random(lights_of(sc), rec.p, rng);
                 else
                     direction = onb_local(uvw, random_cosine_direction(rng));
                 double c = dot(to_unit(direction), uvw.w);
                 double cos_pdf = c <= 0. ? 0. : c / RT_PI;                            /* CosPdf::value, pdf.rs:46-53 */
-                pdf_val = 0.5 * lights_pdf_value(sc, rec.p, direction) + 0.5 * cos_pdf; /* pdf.rs:102-104 */
+                pdf_val = 0.5 * lights_pdf_value(lights_of(sc), rec.p, direction) + 0.5 * cos_pdf; /* pdf.rs:102-104 */
             }
             double cosine = dot(rec.n, to_unit(direction)); /* Lambertian::scattering_pdf, material/mod.rs:58-65 */
             double spdf = cosine < 0. ? 0. : cosine / RT_PI;
@@ -534,9 +557,15 @@ __device__ __forceinline__ void sink_add(const PathSink &sk, uint32_t pixel, int
 }
 
 template <int CLS>
-__global__ void __launch_bounds__(kShadeThreads) k_shade(DScene sc, PathQueue qin, HitBuf hb, PathQueue qout, WaveCtl *ctl, int cur,
+#ifndef RT_SHADE_MIN_BLOCKS
+#define RT_SHADE_MIN_BLOCKS RT_SHADE_BLOCKS_PER_SM
+#endif
+__global__ void __launch_bounds__(kShadeThreads, RT_SHADE_MIN_BLOCKS) k_shade(DScene sc, PathQueue qin, HitBuf hb, PathQueue qout, WaveCtl *ctl, int cur,
                                                     const uint32_t *class_idx, PathSink sk, WaveParams wp, const SortGrid *grid,
                                                     uint32_t *keys_out) {
+    __shared__ uint32_t s_len[RTGPU_MAX_BOUNCE_STATS + 1]; /* paths by length, flushed once per block */
+    for (uint32_t k = threadIdx.x; k <= RTGPU_MAX_BOUNCE_STATS; k += blockDim.x) s_len[k] = 0;
+    __syncthreads();
     uint32_t n = ctl->class_count[CLS];
     uint32_t stride = gridDim.x * blockDim.x;
     uint32_t lane = threadIdx.x & 31u;
@@ -586,7 +615,7 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(DScene sc, PathQueue qi
         {
             uint32_t bin = ended ? (traced < RTGPU_MAX_BOUNCE_STATS ? traced : RTGPU_MAX_BOUNCE_STATS) : 0xffffffffu;
             uint32_t peers = __match_any_sync(0xffffffffu, bin);
-            if (ended && (int)lane == __ffs(peers) - 1) atomicAdd(&ctl->len_hist[bin], (unsigned long long)__popc(peers));
+            if (ended && (int)lane == __ffs(peers) - 1) atomicAdd(&s_len[bin], (uint32_t)__popc(peers));
         }
         if constexpr (CLS != 0) {
             /* compaction: one atomic per warp, survivors packed in lane order */
@@ -605,6 +634,9 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(DScene sc, PathQueue qi
             }
         }
     }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k <= RTGPU_MAX_BOUNCE_STATS; k += blockDim.x)
+        if (s_len[k]) atomicAdd(&ctl->len_hist[k], (unsigned long long)s_len[k]);
 }
 
 /* pixel_color of main.rs:144-151 for the samples of this call: fixed-point sum + large terms, NaN / inf as flagged;
@@ -742,7 +774,7 @@ struct BatchIO {
     }
 };
 template <int NEST>
-__global__ void __launch_bounds__(kThreads, RT_EXTEND_MIN_BLOCKS) k_trace_extend(DScene sc, const rtgpu_ray *rays, const uint64_t *keys, double *t,
+__global__ void __launch_bounds__(kThreads, NEST == 0 ? RT_EXTEND_MIN_BLOCKS0 : RT_EXTEND_MIN_BLOCKS) k_trace_extend(DScene sc, const rtgpu_ray *rays, const uint64_t *keys, double *t,
                                                                    uint32_t *op, uint32_t *rng_pos, uint32_t n, uint32_t *fetch) {
     BatchIO io;
     io.rays = rays;
@@ -947,7 +979,11 @@ rtgpu_status validate(const rtgpu_scene_desc *d, int *medium_nesting) {
             if (!medium_ends.empty() && op.skip > medium_ends.back()) return bad("ConstantMedium boundaries overlap");
             medium_ends.push_back(op.skip);
             if (medium_ends.size() > RT_MAX_MEDIUM_NESTING) return bad("ConstantMedium boundaries nested deeper than RT_MAX_MEDIUM_NESTING");
-            if ((int)medium_ends.size() > *medium_nesting) *medium_nesting = (int)medium_ends.size();
+            {   /* a top-level medium over ONE Sphere is intersected in line (both media of final_scene): it needs no boundary walk */
+                const bool one_sphere = medium_ends.size() == 1 && op.skip == i + 2 && (d->ops[i + 1].kind_ctx & 0xff) == RTGPU_OP_SPHERE;
+                const int need = one_sphere ? 0 : (int)medium_ends.size();
+                if (need > *medium_nesting) *medium_nesting = need;
+            }
             break;
         case RTGPU_OP_PUSH:
             if ((uint64_t)op.a + op.b > d->n_chain) return bad("PUSH chain out of range");
@@ -1212,7 +1248,8 @@ rtgpu_status run_paths(rtgpu_scene *s, const WaveParams &wp, const PathSink &sk,
         if ((st = mark()) != RTGPU_OK) return st;
         if (allow_tail && gen_done && alive_ub <= s->tail_max && it > 0) { /* the few paths that are left run to their end in one launch */
             if (s->medium_nesting > 1) k_tail<2><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->ctl, cur, sk, wp);
-            else k_tail<1><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->ctl, cur, sk, wp);
+            else if (s->medium_nesting == 1) k_tail<1><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->ctl, cur, sk, wp);
+            else k_tail<0><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->ctl, cur, sk, wp);
             k_tail_done<<<1, 1, 0, stream>>>(s->ctl, cur);
             CK(cudaGetLastError());
             if (wt) wt->launches += 2;
@@ -1239,7 +1276,8 @@ rtgpu_status run_paths(rtgpu_scene *s, const WaveParams &wp, const PathSink &sk,
         phase_of_event.push_back(0);
         if ((st = mark()) != RTGPU_OK) return st;
         if (s->medium_nesting > 1) k_extend<2><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->ctl, cur, wp, perm, bound);
-        else k_extend<1><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->ctl, cur, wp, perm, bound);
+        else if (s->medium_nesting == 1) k_extend<1><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->ctl, cur, wp, perm, bound);
+        else k_extend<0><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->ctl, cur, wp, perm, bound);
         CK(cudaGetLastError()); /* a failed extend launch must not let the shade kernels read stale hits */
         phase_of_event.push_back(1);
         if ((st = mark()) != RTGPU_OK) return st;
@@ -1614,6 +1652,8 @@ rtgpu_status rtgpu_trace_batch(rtgpu_scene *s, const rtgpu_ray *rays, int64_t n,
         CK(cudaEventRecord(e0, 0));
         if (s->medium_nesting > 1)
             k_trace_extend<2><<<grid_blocks(s), kThreads>>>(s->d, d_rays, d_keys, d_t, d_u32, d_u32 + n, (uint32_t)n, d_u32 + 2 * n);
+        else if (s->medium_nesting == 0)
+            k_trace_extend<0><<<grid_blocks(s), kThreads>>>(s->d, d_rays, d_keys, d_t, d_u32, d_u32 + n, (uint32_t)n, d_u32 + 2 * n);
         else
             k_trace_extend<1><<<grid_blocks(s), kThreads>>>(s->d, d_rays, d_keys, d_t, d_u32, d_u32 + n, (uint32_t)n, d_u32 + 2 * n);
         CK(cudaEventRecord(e1, 0));
