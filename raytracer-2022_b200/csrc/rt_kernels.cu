@@ -918,8 +918,13 @@ struct rtgpu_scene : WaveRes {
     int medium_nesting = 0; /* deepest ConstantMedium-inside-a-boundary nesting of the program: picks the NEST of the walk kernels */
     int run_ahead = kRunAheadDefault; /* RTGPU_RUN_AHEAD: iterations the host may be ahead of the device (1 .. 32) */
     uint32_t tail_max = 1u << 16; /* RTGPU_TAIL_MAX: at most this many live paths are finished by k_tail in one launch (0 = never) */
-    int sort_mode = 1;          /* RTGPU_SORT_RAYS=0: never reorder rays between bounces */
-    uint32_t sort_min = 1u << 18; /* RTGPU_SORT_MIN: smallest bounce worth a sort (A/B on the B200: 100 K .. 2 M within 1 %) */
+    /* Reordering the rays between bounces pays where a ray meets many ops: C3 (2 961 ops) 99 -> 67 ms in k_extend for 10 ms of sorting;
+     * on the small programs the sort costs more than the walk gains (B200, same build: C2 Cornell, 13 ops, 13.8 ms sorted / 11.4 not;
+     * C1 book-1 scene, 1 506 ops, 15.2 / 14.3; C4 OBJ mesh, 42 556 ops, 28.8 / 28.3).  RTGPU_SORT_RAYS=0 / 1 forces it off / on;
+     * unset, programs of at least RTGPU_SORT_MIN_OPS ops are sorted. */
+    int sort_mode = 1;
+    uint32_t sort_min_ops = 2048;
+    uint32_t sort_min = 1u << 20; /* RTGPU_SORT_MIN: smallest bounce worth a sort (A/B on the B200: 64 K .. 1 M within 1 % on C3, 1 M best on C1, C2, C4) */
 };
 
 namespace {
@@ -1419,6 +1424,8 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
             g_parked_valid[cur] = false;
         }
     }
+    if (const char *e = getenv("RTGPU_SORT_MIN_OPS")) s->sort_min_ops = (uint32_t)atoll(e);
+    s->sort_mode = desc->n_ops >= s->sort_min_ops ? 1 : 0;
     if (const char *e = getenv("RTGPU_SORT_RAYS")) s->sort_mode = atoi(e);
     if (const char *e = getenv("RTGPU_SORT_MIN")) s->sort_min = (uint32_t)atoll(e);
     if (const char *e = getenv("RTGPU_TAIL_MAX")) s->tail_max = (uint32_t)atoll(e);
