@@ -96,8 +96,14 @@ struct rt_rng {
     /* rand: rng.gen_range(0..n) for integers, n >= 1 */
     RT_HD uint32_t gen_index(uint32_t n) {
         uint64_t range = n;
+#if defined(__CUDA_ARCH__)
+        int lz = __clzll((long long)range); /* n >= 1 */
+#elif defined(__GNUC__)
+        int lz = __builtin_clzll(range);
+#else
         int lz = 0;
         for (uint64_t t = range; !(t >> 63); t <<= 1) ++lz;
+#endif
         uint64_t zone = (range << lz) - 1;
         for (;;) {
             uint64_t v = next_u64();

@@ -22,6 +22,7 @@
 #include "../../include/rt_rng.h"
 #include "../../include/rtgpu.h"
 #include "rt_cull.h"
+#include "rt_trig.h"
 
 #define RT_NO_HIT 0xffffffffu
 #ifndef RT_THREADS
@@ -900,9 +901,11 @@ __device__ RT_RECORD_CALL void make_record(const DScene &sc, const Ray &wr, doub
 /* f64 sin/cos expand to ~200 instructions each (plus the Payne-Hanek slow path); one out-of-line copy keeps
  * k_shade small enough for the instruction cache (ncu: `no_instruction` was its top stall). */
 __device__ __noinline__ double rt_sin(double x) { return sin(x); }
-__device__ __noinline__ double2 rt_sincos(double x) { /* (sin, cos), returned in registers */
-    double2 r;
-    sincos(x, &r.x, &r.y);
+/* (sin, cos) of phi = 2 pi r1, r1 in [0, 1): rt_trig.h (0.84 ulp; the general sincos() was a fifth of the Lambertian kernel).
+ * An argument outside [0, 2 pi] cannot come from the two callers; it would give NaN, visibly, not a wrong direction. */
+__device__ __forceinline__ double2 rt_sincos(double phi) {
+    double2 r = make_double2(CUDART_NAN, CUDART_NAN);
+    rt_sincos_2pi(phi, r.x, r.y);
     return r;
 }
 
@@ -951,8 +954,16 @@ __device__ double perlin_turb(const rtgpu_perlin &t, V3 p, int depth) { /* perli
  * compiled out so that the per-material-class shade kernels stay small */
 #define RT_TEXMASK_SIMPLE 0x3 /* SolidColor, CheckerTexture over SolidColors */
 #define RT_TEXMASK_ALL 0xf
+/* in line: with these two out of line the class kernels spill around the calls (A/B on the B200: shade stage of C3 27.9 -> 27.3 ms,
+ * of the Cornell box 5.63 -> 5.28 ms) */
+#ifndef RT_TEX_CALL
+#define RT_TEX_CALL __forceinline__
+#endif
+#ifndef RT_LPDF_CALL
+#define RT_LPDF_CALL __forceinline__
+#endif
 template <int TEXMASK>
-__device__ __noinline__ V3 texture_value(const TexTables sc, uint32_t id, double u, double v, V3 p) {
+__device__ RT_TEX_CALL V3 texture_value(const TexTables sc, uint32_t id, double u, double v, V3 p) {
     for (int depth = 0; depth < 16; ++depth) {
         const rtgpu_texture &t = sc.texs[id];
         uint32_t kind = t.kind;
@@ -1094,7 +1105,7 @@ __device__ __forceinline__ double light_pdf_value(const rtgpu_light &l, V3 o, V3
 /* HittableList::pdf_value (hittable/mod.rs:121-128) over `lights`: the mean of the members' values, a member that is a
  * HittableList contributing the mean over ITS members.  Sums run in member order, as upstream; the recursion is unrolled
  * over an explicit stack (RTGPU_MAX_LIGHT_NESTING levels, checked when the scene is created). */
-__device__ __noinline__ double lights_pdf_value(const LightTable sc, V3 o, V3 v) {
+__device__ RT_LPDF_CALL double lights_pdf_value(const LightTable sc, V3 o, V3 v) {
     if (sc.n_lights == sc.n_light_roots) { /* no HittableList inside `lights` (every reference scene): the same sums without the stack */
         double sum = 0.;
         for (uint32_t k = 0; k < sc.n_light_roots; ++k) sum += light_pdf_value(sc.lights[k], o, v);

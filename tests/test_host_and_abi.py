@@ -272,6 +272,18 @@ def test_f32_box_pretest_never_contradicts_the_f64_test(tmp_path):
     assert unsure < 40.0  # this test set lives on the decision boundary; a render sees ~0.05 % undecided boxes
 
 
+def test_sincos_of_the_direction_sampling_is_within_one_ulp(tmp_path):
+    """rt_trig.h (sin and cos of phi = 2 pi r1 for random_cosine_direction, pdf.rs:12-21, and random_to_sphere, vec.rs:108-117)
+    against long double sinl / cosl on 3 M arguments formed as the callers form them, plus the quadrant boundaries: under one
+    ulp (0.84 measured), i.e. as good as the libm the reference runs on; arguments outside [0, 2 pi] are refused."""
+    exe = str(tmp_path / "trig_fuzz")
+    src = os.path.join(ROOT, "tests", "native", "trig_fuzz.cpp")
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-o", exe, src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, "3", "7"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "outside refused" in r.stdout, r.stdout + r.stderr
+
+
 def test_jpeg_writer_quality_100_roundtrip(tmp_path):
     """The output stage of main.rs:213-221 (JPEG at quality 100): host/jpeg_encode.cpp writes a baseline 4:4:4 stream that
     both this repo's decoder and libjpeg-turbo (PIL) read back to within 4 levels of the input (YCbCr rounding; every
