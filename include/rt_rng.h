@@ -89,6 +89,28 @@ struct rt_rng {
         ++pos;
         return ((uint64_t)hi << 32) | (uint64_t)lo;
     }
+    /* The next THREE slots at once (random_in_unit_sphere draws x, y, z per try): the same values as three next_u64() calls,
+     * but the Philox block that holds the later slots is computed at ONE place by every lane -- three separate calls are three
+     * copies of the generator behind three parity-dependent branches, which a warp of mixed parities executes one after the other. */
+    RT_HD void next3_u64(uint64_t &a, uint64_t &b, uint64_t &c) {
+        const uint32_t b0 = pos >> 1;
+        if (b0 != blk) rt_philox4x32_10(b0, s0, s1, s2, k0, k1, w);
+        uint32_t v[4];
+        rt_philox4x32_10(b0 + 1u, s0, s1, s2, k0, k1, v);
+        if (pos & 1u) {
+            a = ((uint64_t)w[2] << 32) | (uint64_t)w[3];
+            b = ((uint64_t)v[0] << 32) | (uint64_t)v[1];
+            c = ((uint64_t)v[2] << 32) | (uint64_t)v[3];
+        } else {
+            a = ((uint64_t)w[0] << 32) | (uint64_t)w[1];
+            b = ((uint64_t)w[2] << 32) | (uint64_t)w[3];
+            c = ((uint64_t)v[0] << 32) | (uint64_t)v[1];
+        }
+        w[0] = v[0]; w[1] = v[1]; w[2] = v[2]; w[3] = v[3];
+        blk = b0 + 1u;
+        pos += 3u;
+    }
+    static RT_HD double to_unit_f64(uint64_t u) { return (double)(u >> 11) * (1.0 / 9007199254740992.0); }
     /* rand: rng.gen::<f64>() */
     RT_HD double gen() { return (double)(next_u64() >> 11) * (1.0 / 9007199254740992.0); }
     /* rand: rng.gen_range(lo..hi) for f64 */

@@ -1006,9 +1006,11 @@ __device__ RT_TEX_CALL V3 texture_value(const TexTables sc, uint32_t id, double 
 /* ---- random helpers (basic/vec.rs, basic/pdf.rs) --------------------------------------------- */
 __device__ __forceinline__ V3 random_in_unit_sphere(rt_rng &rng) { /* vec.rs:69-76 */
     for (;;) {
-        double x = rng.gen_range(-1., 1.);
-        double y = rng.gen_range(-1., 1.);
-        double z = rng.gen_range(-1., 1.);
+        uint64_t ux, uy, uz;
+        rng.next3_u64(ux, uy, uz); /* = three gen_range(-1, 1) draws, in this order */
+        double x = -1. + (1. - -1.) * rt_rng::to_unit_f64(ux);
+        double y = -1. + (1. - -1.) * rt_rng::to_unit_f64(uy);
+        double z = -1. + (1. - -1.) * rt_rng::to_unit_f64(uz);
         V3 p = v3(x, y, z);
         if (length(p) < 1.) return p;
     }

@@ -79,3 +79,16 @@ def test_gen_index_is_rands_widening_multiply_with_zone_rejection():
                 out.append(m >> 64)
         assert idx.tolist() == out
         assert idx.max() < n
+
+
+def test_next3_hands_out_the_same_slots_as_three_single_draws(tmp_path):
+    """random_in_unit_sphere (vec.rs:69-76) takes its three draws per try through rt_rng::next3_u64 on the device (one converged
+    Philox evaluation instead of three parity-dependent ones): same slots, same order, same generator state afterwards."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "rng_next3")
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(root, "tests", "native", "rng_next3.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "next3 ok" in r.stdout, r.stdout + r.stderr
