@@ -168,6 +168,7 @@ struct WaveCtl {
     uint32_t iter;
     uint32_t n_old; /* entries of the current queue that come from the last bounce (the rest are new camera rays) */
     unsigned long long len_hist[RTGPU_MAX_BOUNCE_STATS + 1]; /* paths by number of segments traced */
+    uint32_t gen_first; /* id of the first path this iteration generates (k_regen makes count[cur] - n_old of them) */
 };
 
 __device__ __forceinline__ void path_rng(rt_rng &rng, const WaveParams &wp, uint32_t pid, uint32_t pos) {
@@ -197,23 +198,23 @@ __device__ __forceinline__ Ray camera_ray(const rtgpu_camera &cam, int x, int y,
 }
 
 /* start of an iteration: the rays of queue `cur` are about to be extended */
-__global__ void k_iter_begin(WaveCtl *ctl, int cur) {
+/* Start of an iteration: resets the per-iteration counters and publishes the length the queue will have once k_regen has
+ * topped it up -- k_regen only fills entries [n_old, count[cur]), so it can run beside the sort of the survivors. */
+__global__ void k_iter_begin(WaveCtl *ctl, int cur, WaveParams wp) {
     if (threadIdx.x == 0) {
         ctl->fetch = 0;
         ctl->count[cur ^ 1] = 0;
         ctl->iter += 1;
+        const uint32_t cnt = ctl->count[cur], first = ctl->gen_next;
+        const uint32_t room = wp.pool > cnt ? wp.pool - cnt : 0u, left = wp.n_paths - first;
+        const uint32_t add = room < left ? room : left;
+        ctl->n_old = cnt;
+        ctl->gen_first = first;
+        ctl->count[cur] = cnt + add;
+        ctl->gen_next = first + add;
+        ctl->rays += (unsigned long long)(cnt + add);
     }
     if (threadIdx.x < 8) ctl->class_count[threadIdx.x] = 0;
-}
-/* after k_regen: the queue is complete; its length is this iteration's ray count */
-__global__ void k_regen_commit(WaveCtl *ctl, int cur, WaveParams wp) {
-    uint32_t cnt = ctl->count[cur];
-    uint32_t room = wp.pool > cnt ? wp.pool - cnt : 0u, left = wp.n_paths - ctl->gen_next;
-    uint32_t add = room < left ? room : left;
-    ctl->n_old = cnt;
-    ctl->count[cur] = cnt + add;
-    ctl->gen_next += add;
-    ctl->rays += (unsigned long long)(cnt + add);
 }
 /* Only the survivors of the last bounce are sorted: the new camera rays behind them are neighbouring pixels already.  The
  * sort runs over a host-side upper bound of the number of survivors; entries past them get the largest key, and since the
@@ -389,11 +390,10 @@ __global__ void k_iota(uint32_t *p, uint32_t n) {
 
 /* Path regeneration: while samples remain, the queue of the coming iteration is topped up to `pool` entries with new
  * camera rays (main.rs:145-149 + Camera::get_ray).  Paths are generated in path-id order = sample-major, so the new
- * rays of one launch are neighbouring pixels of the same sample.  k_regen_commit then publishes the new length. */
+ * rays of one launch are neighbouring pixels of the same sample.  k_iter_begin has published the new length already. */
 __global__ void __launch_bounds__(kThreads) k_regen(DScene sc, PathQueue q, const WaveCtl *ctl, int cur, WaveParams wp) {
-    const uint32_t cnt = ctl->count[cur], first = ctl->gen_next;
-    const uint32_t room = wp.pool > cnt ? wp.pool - cnt : 0u, left = wp.n_paths - first;
-    const uint32_t add = room < left ? room : left;
+    const uint32_t cnt = ctl->n_old, first = ctl->gen_first;
+    const uint32_t add = ctl->count[cur] - cnt;
     uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < add; k += stride) {
         uint32_t pid = first + k;
@@ -728,7 +728,7 @@ __global__ void __launch_bounds__(kThreads) k_tail(DScene sc, PathQueue q, WaveC
         }
         atomicAdd(&ctl->len_hist[traced < RTGPU_MAX_BOUNCE_STATS ? traced : RTGPU_MAX_BOUNCE_STATS], 1ull);
     }
-    /* rays traced here (the iterations count theirs in k_regen_commit) */
+    /* rays traced here (the iterations count theirs in k_iter_begin) */
     for (int o = 16; o > 0; o >>= 1) my_rays += __shfl_xor_sync(0xffffffffu, my_rays, o);
     if ((threadIdx.x & 31) == 0 && my_rays) atomicAdd(&ctl->rays, my_rays);
 }
@@ -862,6 +862,7 @@ struct CtlSnapshot { /* what the host reads back, asynchronously, once per itera
     uint32_t count[2], gen_next, fetch;
 };
 constexpr int kSnapRing = 64;
+constexpr int kSideStreams = 5;
 constexpr int kRunAheadDefault = 2;
 struct WaveRes {
     size_t cap = 0; /* paths the pool can hold */
@@ -893,6 +894,10 @@ struct WaveRes {
     float *accum_dev = nullptr;
     size_t accum_cap = 0;
     std::vector<cudaEvent_t> events;
+    /* side streams: kernels of an iteration that do not depend on each other (k_regen beside the sort, the class kernels beside each
+     * other) are issued on these so that the tail of one fills with the blocks of the next; joined back before anything depends on them */
+    cudaStream_t side[kSideStreams] = {};
+    cudaEvent_t fork_ev = nullptr, side_ev[kSideStreams] = {};
     void release() {
         if (wave_mem) cudaFree(wave_mem);
         if (sink_mem) cudaFree(sink_mem);
@@ -905,6 +910,11 @@ struct WaveRes {
         for (cudaEvent_t e : snap_ev)
             if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : events) cudaEventDestroy(e);
+        for (cudaStream_t st : side)
+            if (st) cudaStreamDestroy(st);
+        for (cudaEvent_t e : side_ev)
+            if (e) cudaEventDestroy(e);
+        if (fork_ev) cudaEventDestroy(fork_ev);
         *this = WaveRes();
     }
 };
@@ -916,6 +926,7 @@ struct rtgpu_scene : WaveRes {
     std::vector<void *> allocs;
     bool class_present[8] = {true, false, false, false, false, false, false, false};
     int medium_nesting = 0; /* deepest ConstantMedium-inside-a-boundary nesting of the program: picks the NEST of the walk kernels */
+    int overlap = 1; /* RTGPU_OVERLAP=0: everything on one stream */
     int run_ahead = kRunAheadDefault; /* RTGPU_RUN_AHEAD: iterations the host may be ahead of the device (1 .. 32) */
     uint32_t tail_max = 1u << 16; /* RTGPU_TAIL_MAX: at most this many live paths are finished by k_tail in one launch (0 = never) */
     /* Reordering the rays between bounces pays where a ray meets many ops: C3 (2 961 ops) 99 -> 67 ms in k_extend for 10 ms of sorting;
@@ -1217,6 +1228,14 @@ rtgpu_status run_paths(rtgpu_scene *s, const WaveParams &wp, const PathSink &sk,
     if (st != RTGPU_OK) return st;
     if (wp.n_paths == 0 || wp.max_depth == 0) return RTGPU_OK; /* depth 0: every ray_color call returns black (main.rs:240-242) */
     CK(cudaMemsetAsync(s->ctl, 0, sizeof(WaveCtl), stream));
+    const bool overlap = s->overlap != 0;
+    if (overlap && !s->fork_ev) {
+        CK(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
+        for (int k = 0; k < kSideStreams; ++k) {
+            CK(cudaStreamCreateWithFlags(&s->side[k], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&s->side_ev[k], cudaEventDisableTiming));
+        }
+    }
     const int blocks = grid_blocks(s);
     const uint32_t cap = (uint32_t)s->cap;
     bool sorting = s->sort_mode != 0 && wp.n_paths >= s->sort_min && wp.max_depth > 1;
@@ -1263,14 +1282,21 @@ rtgpu_status run_paths(rtgpu_scene *s, const WaveParams &wp, const PathSink &sk,
             tail_ran = true;
             break;
         }
-        k_iter_begin<<<1, 32, 0, stream>>>(s->ctl, cur);
-        if (!gen_done) {
-            k_regen<<<blocks, kThreads, 0, stream>>>(s->d, qin, s->ctl, cur, wp);
+        k_iter_begin<<<1, 32, 0, stream>>>(s->ctl, cur, wp);
+        const bool sort_now = sorting && it >= 1 && bound >= s->sort_min;
+        bool regen_aside = false;
+        if (!gen_done) { /* new camera rays go behind the survivors: beside the sort of the survivors when there is one */
+            regen_aside = overlap && sort_now;
+            if (regen_aside) {
+                CK(cudaEventRecord(s->fork_ev, stream));
+                CK(cudaStreamWaitEvent(s->side[0], s->fork_ev, 0));
+            }
+            k_regen<<<blocks, kThreads, 0, regen_aside ? s->side[0] : stream>>>(s->d, qin, s->ctl, cur, wp);
+            if (regen_aside) CK(cudaEventRecord(s->side_ev[0], s->side[0]));
             if (wt) wt->launches += 1;
         }
-        k_regen_commit<<<1, 1, 0, stream>>>(s->ctl, cur, wp);
         const uint32_t *perm = nullptr;
-        if (sorting && it >= 1 && bound >= s->sort_min) {
+        if (sort_now) {
             k_pad_keys<<<blocks, 256, 0, stream>>>(s->ctl, s->sort_keys[0], bound);
             size_t tb = s->sort_temp_bytes;
             CK(cub::DeviceRadixSort::SortPairs(s->sort_temp, tb, s->sort_keys[0], s->sort_keys[1], s->sort_idx[0], s->sort_idx[1], (int)bound, 0,
@@ -1278,6 +1304,7 @@ rtgpu_status run_paths(rtgpu_scene *s, const WaveParams &wp, const PathSink &sk,
             perm = s->sort_idx[1]; /* (the library's sort kernels are not counted in stats->launches: those are this file's) */
             if (wt) wt->launches += 1;
         }
+        if (regen_aside) CK(cudaStreamWaitEvent(stream, s->side_ev[0], 0));
         phase_of_event.push_back(0);
         if ((st = mark()) != RTGPU_OK) return st;
         if (s->medium_nesting > 1) k_extend<2><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->ctl, cur, wp, perm, bound);
@@ -1294,17 +1321,34 @@ rtgpu_status run_paths(rtgpu_scene *s, const WaveParams &wp, const PathSink &sk,
         }
         {
             k_classify<<<blocks, 256, 0, stream>>>(s->hb, s->ctl, cur, s->class_idx, cap);
+            /* the class kernels read disjoint lists and append to the out queue through one atomic cursor: independent of each other.
+             * Class 1 (the largest) stays on the caller's stream, the others go to side streams and are joined below. */
+            int n_side = 0;
+            if (overlap) CK(cudaEventRecord(s->fork_ev, stream));
 #define RT_SHADE(C)                                                                                                                     \
-    k_shade<C><<<s->n_sm * RT_SHADE_BLOCKS_PER_SM, kShadeThreads, 0, stream>>>(s->d, qin, s->hb, qout, s->ctl, cur, s->class_idx + (size_t)C * cap, sk, \
-                                                                            wp, grid, sorting ? s->sort_keys[0] : nullptr)
+    do {                                                                                                                                \
+        cudaStream_t cs = stream;                                                                                                       \
+        if (overlap && C != 1) {                                                                                                        \
+            cs = s->side[n_side];                                                                                                       \
+            CK(cudaStreamWaitEvent(cs, s->fork_ev, 0));                                                                                 \
+        }                                                                                                                               \
+        k_shade<C><<<s->n_sm * RT_SHADE_BLOCKS_PER_SM, kShadeThreads, 0, cs>>>(s->d, qin, s->hb, qout, s->ctl, cur,                     \
+                                                                                s->class_idx + (size_t)C * cap, sk, wp, grid,            \
+                                                                                sorting ? s->sort_keys[0] : nullptr);                    \
+        if (overlap && C != 1) {                                                                                                        \
+            CK(cudaEventRecord(s->side_ev[n_side], cs));                                                                                \
+            ++n_side;                                                                                                                   \
+        }                                                                                                                               \
+    } while (0)
             int n_launched = 0;
-            RT_SHADE(0);
             if (s->class_present[1]) { RT_SHADE(1); ++n_launched; }
-            if (s->class_present[2]) { RT_SHADE(2); ++n_launched; }
-            if (s->class_present[3]) { RT_SHADE(3); ++n_launched; }
-            if (s->class_present[4]) { RT_SHADE(4); ++n_launched; }
             if (s->class_present[5]) { RT_SHADE(5); ++n_launched; }
-            if (wt) wt->launches += 5 + (uint64_t)n_launched; /* iter_begin, commit, extend, classify, class 0 + the others */
+            if (s->class_present[2]) { RT_SHADE(2); ++n_launched; }
+            RT_SHADE(0);
+            if (s->class_present[4]) { RT_SHADE(4); ++n_launched; }
+            if (s->class_present[3]) { RT_SHADE(3); ++n_launched; }
+            for (int k = 0; k < n_side; ++k) CK(cudaStreamWaitEvent(stream, s->side_ev[k], 0));
+            if (wt) wt->launches += 4 + (uint64_t)n_launched; /* iter_begin, extend, classify, class 0 + the others */
 #undef RT_SHADE
         }
         phase_of_event.push_back(2);
@@ -1424,6 +1468,7 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
             g_parked_valid[cur] = false;
         }
     }
+    if (const char *e = getenv("RTGPU_OVERLAP")) s->overlap = atoi(e);
     if (const char *e = getenv("RTGPU_SORT_MIN_OPS")) s->sort_min_ops = (uint32_t)atoll(e);
     s->sort_mode = desc->n_ops >= s->sort_min_ops ? 1 : 0;
     if (const char *e = getenv("RTGPU_SORT_RAYS")) s->sort_mode = atoi(e);
