@@ -325,6 +325,27 @@ def test_tail_kernel_gives_the_same_image(name, monkeypatch):
         assert st1.launches_extend < st0.launches_extend
 
 
+@pytest.mark.parametrize("name", ["final_scene", "cornell_smoke"])
+def test_side_streams_give_the_same_image(name, monkeypatch):
+    """k_regen runs beside the sort of the survivors and the six class kernels beside each other, on side streams of the scene
+    (RTGPU_OVERLAP, default on).  Survivors then reach the out queue in another order, which nothing may depend on: the
+    accumulation buffer, the ray count and the rays per bounce must be BIT-identical to the single-stream render -- with a pool
+    small enough that paths are regenerated and (sort forced on) survivors sorted while k_regen runs."""
+    s, orc, _ = get(name)
+    w, h, spp = 200, 160, 12
+    out = {}
+    monkeypatch.setenv("RTGPU_SORT_RAYS", "1")
+    monkeypatch.setenv("RTGPU_SORT_MIN", "1000")
+    for mode in ("0", "1"):
+        monkeypatch.setenv("RTGPU_OVERLAP", mode)
+        gpu = rt.GpuScene(s.lower(), device=0)  # the switches are read when the scene is created
+        out[mode] = gpu.render(w, h, 0, spp, seed=33, max_paths_in_flight=w * h * 2)
+        gpu.close()
+    (a0, st0), (a1, st1) = out["0"], out["1"]
+    assert st0.rays == st1.rays and list(st0.rays_per_bounce) == list(st1.rays_per_bounce)
+    assert np.array_equal(a0, a1)
+
+
 def test_many_samples_run_in_several_passes(monkeypatch):
     """A render call covers its sample range in passes of at most 32768 spp and fewer than 2^32 paths (C5 at 10 000 spp: 20 passes of
     517 spp); every pass adds its exact pixel sums to the caller's buffer.  Forced to 3 spp per pass on a small image: the same
