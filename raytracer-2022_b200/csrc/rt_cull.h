@@ -101,6 +101,15 @@ RT_CULL_HD void cull_ray_setup(CullRay &c, double ox, double oy, double oz, doub
     c.tmin = (float)tmin;
 }
 
+/* The same ray queried with another t_min (a ConstantMedium asks its boundary from -inf, then from t1 + 0.0001): the slab terms of
+ * e2 do not depend on t_min, so adding the new t_min's share to the old margin -- which still holds the old t_min's -- gives a
+ * valid, slightly larger margin without the three reciprocals of cull_ray_setup.  Larger only means more RT_CULL_UNSURE. */
+RT_CULL_HD void cull_ray_retime(CullRay &c, double tmin) {
+    double e2 = (double)c.e2 + (fabs(tmin) <= 1.7e308 ? 2.6e-7 * fabs(tmin) : 0.);
+    c.e2 = tmin == tmin ? rt_f32_up(e2) : INFINITY; /* (inf stays inf) */
+    c.tmin = (float)tmin;
+}
+
 /* box = f32(min.xyz), f32(max.xyz) of the node;  bestL <= running best <= bestU */
 RT_CULL_HD int cull_box(const CullRay &c, float b0, float b1, float b2, float b3, float b4, float b5, float bestL, float bestU) {
     float lx = fmaf(b0, c.ix, c.nx), hx = fmaf(b3, c.ix, c.nx);

@@ -31,6 +31,7 @@
 #define RT_MAX_PUSH 4   /* nesting of PUSH ops (instances inside instances) */
 #define RT_MAX_CHAIN 8  /* wrappers around one primitive */
 #define RT_CLASS_ISOTROPIC 5u  /* shade classes: see k_classify in rt_kernels.cu */
+#define RT_KIND_PASS_END 13u /* in registers only: the cursor of a lane that walks a medium's boundary in the warp loop reached its end */
 #define RT_KIND_UNSURE_NODE 12u /* in registers only: a fetched NODE whose box the f32 pre-test could not decide */
 #define RT_PI 3.14159265358979323846264338327950288
 #define RT_F64_MAX 1.7976931348623157e308
@@ -267,6 +268,7 @@ struct Closest {
  * Traversal<RayRegs> is the single-ray walk with everything in registers: it runs the boundary of a ConstantMedium
  * that is not one sphere (closest_hit_boundary).  The main walk of k_extend is extend_cta_loop below, which keeps its
  * rays in shared memory and uses the same tests phase by phase. */
+#define RT_MAX_MEDIUM_NESTING 2 /* a ConstantMedium inside the boundary of a ConstantMedium, and no deeper (kernels: NEST 1, 2) */
 /* CONST_TMIN: t_min is the 0.001 of main.rs:243 for every ray (k_extend), which saves its two registers */
 template <bool CONST_TMIN>
 struct RayRegsT {
@@ -281,6 +283,9 @@ struct RayRegsT {
         tm_ = tm;
         if (!CONST_TMIN) tmin_ = tmin;
     }
+    __device__ __forceinline__ void set_tmin(double tmin) {
+        if (!CONST_TMIN) tmin_ = tmin;
+    }
 };
 typedef RayRegsT<false> RayRegs;
 #ifndef RT_NODE_FETCH32
@@ -292,7 +297,6 @@ typedef RayRegsT<false> RayRegs;
                           second test is wasted whenever the first box is missed) */
 #endif
 
-#define RT_MAX_MEDIUM_NESTING 2 /* a ConstantMedium inside the boundary of a ConstantMedium, and no deeper (kernels: NEST 1, 2) */
 /* Where a walk draws its uniforms from: a VALUE type with `double operator()()` and a stream position `pos`.  It is handed to
  * the out-of-line boundary walk by value and the position comes back in the result: taking the address of the caller's state
  * would push it into local memory for the whole kernel. */
@@ -312,9 +316,10 @@ struct StreamDraw {
     }
     __device__ __forceinline__ StreamDraw stream() const { return *this; }
 };
-/* NEST = how many levels of ConstantMedium boundaries the instantiation walks.  Kernels exist for NEST 1 and 2: the mere presence
- * of the LEVEL 2 walk behind the out-of-line call makes ptxas keep the warp loop's state in local memory (k_extend 2x slower,
- * measured), so scenes without a medium inside a medium's boundary -- all of the reference's -- run the NEST 1 kernels. */
+/* The out-of-line boundary walk of the SINGLE-RAY walkers (k_tail, and itself for a medium inside a medium's boundary): NEST = how
+ * many levels of boundaries the instantiation walks (LEVEL < NEST calls LEVEL + 1).  The warp loop of k_extend does not use it: a
+ * call there shapes the register allocation of the whole kernel, so its lanes walk boundaries themselves
+ * (Traversal<.., WALK_IN_LOOP>). */
 #ifndef RT_BOUNDARY_CALL
 #define RT_BOUNDARY_CALL __noinline__
 #endif
@@ -325,13 +330,22 @@ __device__ RT_BOUNDARY_CALL BoundaryHit closest_hit_boundary(const TravScene sc,
 /* phases of the warp scheduler: ops whose code is the same run together */
 enum { PH_NODE = 0, PH_SPHERE = 1, PH_BOX = 2, PH_TRI = 3, PH_MISC = 4, PH_EXACT = 5, PH_NONE = 7 };
 __device__ __forceinline__ uint32_t phase_of_kind(uint32_t kind) {
-    /* NODE SPHERE MSPHERE RECT_XY RECT_XZ RECT_YZ BOX TRI MEDIUM PUSH POP RING UNSURE_NODE, 3 bits each */
-    return (uint32_t)((05444432444110ull >> (3 * kind)) & 7ull);
+    /* NODE SPHERE MSPHERE RECT_XY RECT_XZ RECT_YZ BOX TRI MEDIUM PUSH POP RING UNSURE_NODE PASS_END, 3 bits each */
+    return (uint32_t)((045444432444110ull >> (3 * kind)) & 7ull);
 }
 
 struct SavedRays {
     double v[RT_MAX_PUSH][6];
     float c[RT_MAX_PUSH][8]; /* the outer ray's CullRay: cheaper to keep than three divisions at the POP */
+};
+/* What a lane of the warp loop puts away while it walks the boundary of a ConstantMedium (Traversal<RS, true>): the outer walk's
+ * running best, t_min and range end, and what ConstantMedium::hit needs once both boundary hits are known.  Indexed by the
+ * nesting depth, hence in local memory like SavedRays; touched twice per walked medium. */
+struct MediumFrames {
+    double best_t[RT_MAX_MEDIUM_NESTING], tmin[RT_MAX_MEDIUM_NESTING], t1[RT_MAX_MEDIUM_NESTING], neg_inv_density[RT_MAX_MEDIUM_NESTING];
+    float cull_e2[RT_MAX_MEDIUM_NESTING], cull_tmin[RT_MAX_MEDIUM_NESTING]; /* the outer walk's margin and t_min of the box pre-test */
+    uint32_t best_op[RT_MAX_MEDIUM_NESTING], best_face_cls[RT_MAX_MEDIUM_NESTING], lim[RT_MAX_MEDIUM_NESTING], op[RT_MAX_MEDIUM_NESTING],
+        skip[RT_MAX_MEDIUM_NESTING], pass[RT_MAX_MEDIUM_NESTING];
 };
 
 __device__ __forceinline__ float lo_f32(double x) { return __int_as_float(__double2loint(x)); }
@@ -341,7 +355,11 @@ __device__ __forceinline__ float hi_f32(double x) { return __int_as_float(__doub
  * together) are fetched as soon as the index is known; exec_*() consume them.
  * One call of exec handles one op, so a warp can run "all lanes that sit on a NODE" together,
  * then "all lanes that sit on a sphere", ... (see extend_warp_loop). */
-template <typename RS>
+/* WALK_IN_LOOP (the warp loop of scenes with walked media): a ConstantMedium whose boundary is not one Sphere does not call
+ * closest_hit_boundary; the lane puts its outer best / t_min away (MediumFrames), walks the boundary's ops through the very same
+ * NODE and leaf rounds -- once from -inf, once from t1 + 0.0001 (constantmedium.rs:50-58) -- and picks the outer walk up again.
+ * No call in the loop (what a call costs there: DESIGN.md 5), and the boundary's boxes, rects and wrappers run warp-wide. */
+template <typename RS, bool WALK_IN_LOOP = false>
 struct Traversal {
     RS ray;             /* f64 origin, direction, shutter time, t_min */
     CullRay c;          /* f32 view for the box pre-test (rt_cull.h) */
@@ -349,6 +367,8 @@ struct Traversal {
     Closest best;
     uint32_t i;
     int sp;
+    uint32_t lim; /* WALK_IN_LOOP: end of the boundary being walked (0xffffffff outside of one) */
+    int md;       /* WALK_IN_LOOP: boundaries being walked (depth of MediumFrames) */
     uint4 h;     /* bytes 0..15 of unit i: header of a leaf op / kind|ordinal, skip, box min.xy of a NODE */
     double p[6]; /* bytes 16..63: payload of a leaf op / rest of the NODE box, then unit i+1 */
     /* the PUSH/POP stack lives OUTSIDE this struct (SavedRays): it is indexed dynamically, and an
@@ -357,6 +377,12 @@ struct Traversal {
     /* fetched as soon as the index is known: the L1/L2 latency of the next op overlaps with the warp
      * vote and with the other lanes' work */
     __device__ __forceinline__ void fetch_op(const TravScene sc) {
+        if constexpr (WALK_IN_LOOP) {
+            if (i == lim) { /* ops of a boundary never jump past its end: the pass is over */
+                h.x = RT_KIND_PASS_END;
+                return;
+            }
+        }
         if (i < sc.end) {
             const uint4 *op = unit_ptr(sc.prog, i);
             h = load_op_header(op);
@@ -395,9 +421,74 @@ struct Traversal {
         set_best_bounds();
         i = begin;
         sp = 0;
+        lim = 0xffffffffu;
+        md = 0;
         fetch_op(sc);
     }
-    __device__ __forceinline__ bool done(const TravScene sc) const { return i >= sc.end; }
+    __device__ __forceinline__ bool done(const TravScene sc) const {
+        if constexpr (WALK_IN_LOOP) return i >= sc.end && md == 0; /* a boundary may end where the program ends */
+        else return i >= sc.end;
+    }
+    /* WALK_IN_LOOP: (re)starts a pass over the boundary [begin, lim) with a fresh best and the given t_min */
+    __device__ __forceinline__ void start_pass(const TravScene sc, uint32_t begin, double tmin) {
+        best.t = CUDART_INF;
+        best.op = RT_NO_HIT;
+        best.face = 0;
+        best.cls = 0;
+        ray.set_tmin(tmin);
+        cull_ray_retime(c, tmin);
+        set_best_bounds();
+        i = begin;
+        fetch_op(sc);
+    }
+    /* the MEDIUM op under the cursor has a boundary to walk: put the outer walk away and start the first pass */
+    __device__ __forceinline__ void begin_boundary(const TravScene sc, MediumFrames &mf) {
+        mf.best_t[md] = best.t;
+        mf.best_op[md] = best.op;
+        mf.best_face_cls[md] = best.face | (best.cls << 8);
+        mf.tmin[md] = ray.tmin();
+        mf.cull_e2[md] = c.e2;
+        mf.cull_tmin[md] = c.tmin;
+        mf.lim[md] = lim;
+        mf.op[md] = i;
+        mf.skip[md] = h.y;
+        mf.neg_inv_density[md] = p[0];
+        mf.pass[md] = 1;
+        ++md;
+        lim = h.y;
+        start_pass(sc, i + 2, -CUDART_INF);
+    }
+    /* the cursor reached the end of the boundary (kind PASS_END) */
+    template <typename DS>
+    __device__ __forceinline__ void end_pass(const TravScene sc, MediumFrames &mf, DS &draw) {
+        const int k = md - 1;
+        const bool first = mf.pass[k] == 1;
+        if (first && best.op != RT_NO_HIT) { /* rec1 found: look for rec2 from rec1.t + 0.0001 */
+            mf.t1[k] = best.t;
+            mf.pass[k] = 2;
+            start_pass(sc, mf.op[k] + 2, best.t + 0.0001);
+            return;
+        }
+        const bool h1 = !first, h2 = !first && best.op != RT_NO_HIT;
+        const double t1 = h1 ? mf.t1[k] : CUDART_INF, t2 = best.t;
+        /* back to the outer walk */
+        best.t = mf.best_t[k];
+        best.op = mf.best_op[k];
+        best.face = mf.best_face_cls[k] & 0xffu;
+        best.cls = mf.best_face_cls[k] >> 8;
+        ray.set_tmin(mf.tmin[k]);
+        c.e2 = mf.cull_e2[k];
+        c.tmin = mf.cull_tmin[k];
+        lim = mf.lim[k];
+        md = k;
+        i = mf.op[k];
+        p[0] = mf.neg_inv_density[k];
+        const bool hit = medium_decide(length_sqr(ray.d()), ray.tmin(), h1, t1, h2, t2, draw);
+        i = mf.skip[k];
+        (void)hit;
+        set_best_bounds();
+        fetch_op(sc);
+    }
     __device__ __forceinline__ uint32_t phase() const { return phase_of_kind(h.x & 0xffu); }
     __device__ __forceinline__ bool at_node() const { return (h.x & 0xffu) == RTGPU_OP_NODE; } /* = phase() == PH_NODE, two instructions */
 
@@ -473,11 +564,39 @@ struct Traversal {
         i += 4;
         fetch_op(sc);
     }
+    /* ConstantMedium::hit once the two boundary hits are known (constantmedium.rs:60-83); a = |d|^2, p[0] = -1/density, i = the op */
+    template <typename DS>
+    __device__ __forceinline__ bool medium_decide(double a, double tmin, bool h1, double t1, bool h2, double t2, DS &draw) {
+        if (h1 && h2) {
+            t1 = fmax(t1, tmin);
+            t2 = fmin(t2, best.t);
+            if (!(t1 >= t2)) {
+                t1 = fmax(t1, 0.);
+                double ray_length = sqrt(a);
+                double distance_inside_boundary = (t2 - t1) * ray_length;
+                double rnd = draw();
+                double hit_distance = p[0] * log(rnd); /* neg_inv_density * rnd.log(E) */
+                if (!(hit_distance > distance_inside_boundary)) {
+                    best.t = t1 + hit_distance / ray_length;
+                    best.op = i;
+                    best.cls = RT_CLASS_ISOTROPIC; /* a ConstantMedium scatters with its Isotropic material (constantmedium.rs:77) */
+                    return true;
+                }
+            }
+        }
+        return false;
+    }
     /* rects, ConstantMedium, PUSH, POP.  DRAW() = next uniform of the ray's stream */
     template <int LEVEL, int NEST, typename DS>
-    __device__ __forceinline__ void exec_misc(const TravScene sc, SavedRays &stk, DS &draw) {
+    __device__ __forceinline__ void exec_misc(const TravScene sc, SavedRays &stk, DS &draw, MediumFrames *mf = nullptr) {
         bool hit = false;
         const uint32_t kind = h.x & 0xffu;
+        if constexpr (WALK_IN_LOOP) {
+            if (kind == RT_KIND_PASS_END) {
+                end_pass(sc, *mf, draw);
+                return;
+            }
+        }
         if (kind == RTGPU_OP_POP) {
             --sp;
             ray.set_od(v3(stk.v[sp][0], stk.v[sp][1], stk.v[sp][2]), v3(stk.v[sp][3], stk.v[sp][4], stk.v[sp][5]));
@@ -524,6 +643,9 @@ struct Traversal {
                     V3 c0 = v3(bp[0], bp[1], bp[2]);
                     h1 = hit_sphere(o, d, a, c0, bp[3], -CUDART_INF, t1);
                     if (h1) h2 = hit_sphere(o, d, a, c0, bp[3], t1 + 0.0001, t2);
+                } else if constexpr (WALK_IN_LOOP) {
+                    begin_boundary(sc, *mf);
+                    return;
                 } else if constexpr (LEVEL < NEST) {
                     const double tm = ray.tm();
                     BoundaryHit r1 = closest_hit_boundary<LEVEL + 1, NEST>(sc, i + 2, h.y, o, d, tm, -CUDART_INF, CUDART_INF, draw.stream());
@@ -539,23 +661,7 @@ struct Traversal {
                 } else {
                     h1 = false; /* NEST 0: rtgpu_scene_create found every boundary to be one Sphere */
                 }
-                if (h1 && h2) {
-                    t1 = fmax(t1, tmin);
-                    t2 = fmin(t2, best.t);
-                    if (!(t1 >= t2)) {
-                        t1 = fmax(t1, 0.);
-                        double ray_length = sqrt(a);
-                        double distance_inside_boundary = (t2 - t1) * ray_length;
-                        double rnd = draw();
-                        double hit_distance = p[0] * log(rnd); /* neg_inv_density * rnd.log(E) */
-                        if (!(hit_distance > distance_inside_boundary)) {
-                            best.t = t1 + hit_distance / ray_length;
-                            best.op = i;
-                            best.cls = RT_CLASS_ISOTROPIC; /* a ConstantMedium scatters with its Isotropic material (constantmedium.rs:77) */
-                            hit = true;
-                        }
-                    }
-                }
+                hit = medium_decide(a, tmin, h1, t1, h2, t2, draw);
             }
             i = h.y;
             break;
@@ -653,8 +759,10 @@ struct LaneDraw {
 template <int NEST, typename IO>
 __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_units, uint32_t n, uint32_t *fetch, IO &io) {
     const uint32_t lane = threadIdx.x & 31u;
-    Traversal<RayRegsT<IO::kConstTmin>> tr;
+    constexpr bool kWalkInLoop = NEST >= 1; /* scenes with walked media: boundaries are walked by this loop, t_min varies */
+    Traversal<RayRegsT<IO::kConstTmin && !kWalkInLoop>, kWalkInLoop> tr;
     SavedRays stk;
+    MediumFrames mf;
     bool active = false, exhausted = false;
     uint32_t rng_a = 0, rng_b = 0, rng_pos = 0, cur = 0;
     const int refill_at = io.refill_at();
@@ -737,7 +845,7 @@ __device__ __forceinline__ void extend_warp_loop(const TravScene ts, uint32_t n_
             case PH_TRI: tr.exec_tri(ts); break;
             default: {
                 LaneDraw<IO> draw{io, rng_a, rng_b, rng_pos};
-                tr.template exec_misc<0, NEST>(ts, stk, draw);
+                tr.template exec_misc<0, NEST>(ts, stk, draw, &mf);
                 rng_pos = draw.pos;
                 break;
             }

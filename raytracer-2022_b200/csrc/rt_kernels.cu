@@ -225,7 +225,8 @@ __global__ void k_pad_keys(const WaveCtl *ctl, uint32_t *keys, uint32_t pad_to) 
 }
 /* world.hit(r, 0.001, f64::MAX), main.rs:243 -- persistent warps, see extend_warp_loop */
 #ifndef RT_EXTEND_MIN_BLOCKS
-#define RT_EXTEND_MIN_BLOCKS 4 /* NEST >= 1: the out-of-line boundary walk costs the warp loop ~20 registers of spills even at 128 */
+#define RT_EXTEND_MIN_BLOCKS 5 /* NEST 1 (boundaries walked by the loop: a variable t_min, a range end and a depth per lane): 96 registers,
+                                 20 warps/SM -- cornell_smoke, ms in k_extend: 4: 26.0, 5: 24.9, 6: 25.5 (with the out-of-line walk: 29.0) */
 #endif
 #ifndef RT_EXTEND_MIN_BLOCKS0
 #define RT_EXTEND_MIN_BLOCKS0 7 /* NEST 0 (no call in the loop): 72 registers, 28 warps/SM -- A/B on C3 (64 spp), ms in k_extend:
@@ -281,7 +282,8 @@ struct QueueIO {
 #endif
     }
 };
-/* NEST: see closest_hit_boundary (rt_device.cuh) -- 1 for every scene without a medium inside a medium's boundary */
+/* NEST 0: every ConstantMedium of the scene is bounded by one Sphere (intersected in line); NEST 1: some boundary has to be walked,
+ * and the warp loop does it itself (Traversal<.., WALK_IN_LOOP>, any depth up to RT_MAX_MEDIUM_NESTING).  Picked at rtgpu_scene_create. */
 template <int NEST>
 __global__ void __launch_bounds__(kThreads, NEST == 0 ? RT_EXTEND_MIN_BLOCKS0 : RT_EXTEND_MIN_BLOCKS) k_extend(DScene sc, PathQueue q, HitBuf hb, WaveCtl *ctl, int cur,
                                                                            WaveParams wp, const uint32_t *perm, uint32_t n_perm) {
@@ -310,6 +312,9 @@ struct SortGrid {
 };
 #ifndef RT_SORT_CELL_BITS
 #define RT_SORT_CELL_BITS 7 /* origin cells per axis = 2^bits */
+#endif
+#ifndef RT_SORT_SIGMAS
+#define RT_SORT_SIGMAS 2.5 /* half-width of the cell grid in standard deviations of the first hit points */
 #endif
 #ifndef RT_SORT_DIR_BITS
 #define RT_SORT_DIR_BITS 8 /* direction below the octant: 8, 10, 12 = major axis + 2 x (3, 4, 5) bits, 6 = 2 x 3 bits, 0 = octant only */
@@ -378,8 +383,8 @@ __global__ void k_sort_grid(const double *moments, SortGrid *g) {
         double cnt = fmax(moments[6], 1.);
         double mean = moments[c] / cnt;
         double sd = sqrt(fmax(moments[3 + c] / cnt - mean * mean, 0.));
-        g->lo[c] = (float)(mean - 2.5 * sd);
-        float ext = (float)(5.0 * sd);
+        g->lo[c] = (float)(mean - RT_SORT_SIGMAS * sd);
+        float ext = (float)(2. * RT_SORT_SIGMAS * sd);
         g->inv[c] = ext > 0.f ? ((float)(1 << RT_SORT_CELL_BITS) - 0.001f) / ext : 0.f;
     }
 }
@@ -1307,8 +1312,7 @@ rtgpu_status run_paths(rtgpu_scene *s, const WaveParams &wp, const PathSink &sk,
         if (regen_aside) CK(cudaStreamWaitEvent(stream, s->side_ev[0], 0));
         phase_of_event.push_back(0);
         if ((st = mark()) != RTGPU_OK) return st;
-        if (s->medium_nesting > 1) k_extend<2><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->ctl, cur, wp, perm, bound);
-        else if (s->medium_nesting == 1) k_extend<1><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->ctl, cur, wp, perm, bound);
+        if (s->medium_nesting >= 1) k_extend<1><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->ctl, cur, wp, perm, bound);
         else k_extend<0><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->ctl, cur, wp, perm, bound);
         CK(cudaGetLastError()); /* a failed extend launch must not let the shade kernels read stale hits */
         phase_of_event.push_back(1);
@@ -1702,9 +1706,7 @@ rtgpu_status rtgpu_trace_batch(rtgpu_scene *s, const rtgpu_ray *rays, int64_t n,
         CK(cudaEventCreate(&e0));
         CK(cudaEventCreate(&e1));
         CK(cudaEventRecord(e0, 0));
-        if (s->medium_nesting > 1)
-            k_trace_extend<2><<<grid_blocks(s), kThreads>>>(s->d, d_rays, d_keys, d_t, d_u32, d_u32 + n, (uint32_t)n, d_u32 + 2 * n);
-        else if (s->medium_nesting == 0)
+        if (s->medium_nesting == 0)
             k_trace_extend<0><<<grid_blocks(s), kThreads>>>(s->d, d_rays, d_keys, d_t, d_u32, d_u32 + n, (uint32_t)n, d_u32 + 2 * n);
         else
             k_trace_extend<1><<<grid_blocks(s), kThreads>>>(s->d, d_rays, d_keys, d_t, d_u32, d_u32 + n, (uint32_t)n, d_u32 + 2 * n);

@@ -66,7 +66,16 @@ int main(int argc, char **argv) {
         float extent = (float)std::fmax((double)RT_CULL_MIN_EXTENT, bmax * (1. + U(rng)));
         extent = rt_f32_up((double)extent);
         CullRay c;
-        cull_ray_setup(c, o[0], o[1], o[2], inv[0], inv[1], inv[2], t_min, extent);
+        if ((it & 3) == 3) {
+            /* the same ray set up for another t_min and then re-timed (cull_ray_retime: a ConstantMedium asks its boundary from -inf,
+             * then from t1 + 0.0001, while the lane keeps its ray): the answer must hold for the t_min it was re-timed to */
+            double other = (it & 128) ? 0.001 : ((it & 256) ? -INFINITY : U(rng) * 3.);
+            cull_ray_setup(c, o[0], o[1], o[2], inv[0], inv[1], inv[2], other, extent);
+            if (it & 512) cull_ray_retime(c, -INFINITY); /* two re-timings in a row, as in the two passes over a boundary */
+            cull_ray_retime(c, t_min);
+        } else {
+            cull_ray_setup(c, o[0], o[1], o[2], inv[0], inv[1], inv[2], t_min, extent);
+        }
         int r = cull_box(c, (float)mn[0], (float)mn[1], (float)mn[2], (float)mx[0], (float)mx[1], (float)mx[2], rt_f32_down(best), rt_f32_up(best));
         bool ref = aabb_hit_ref(mn, mx, o, d, t_min, best);
         cnt[r]++;
