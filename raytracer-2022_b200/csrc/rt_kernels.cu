@@ -2,13 +2,15 @@
  * rt_kernels.cu -- wavefront path tracer for sm_100a and the C ABI of include/rtgpu.h.
  *
  * A render keeps a bounded POOL of paths in flight (path regeneration): one queue entry per live path, two queues
- * that swap roles.  Per iteration, all on one stream and without a host round trip:
+ * that swap roles.  Per iteration, in stream order and without a host round trip (kernels that do not depend on each other --
+ * k_regen and the sort, the class kernels among themselves -- go to side streams and are joined with events):
  *
- *   k_iter_begin  resets the per-iteration counters on the device
+ *   k_iter_begin  resets the per-iteration counters on the device and publishes the length the queue is topped up to
  *   k_regen       tops the queue up with new camera rays while samples remain (main.rs:145-149, camera.rs:64-73),
  *                 so every launch below carries a full queue whatever the depth of its paths
- *   (sort)        the queue is walked in the order of a 32-bit origin-cell / direction key that k_regen and the
- *                 shade kernels wrote next to every ray; only (key, entry) pairs are sorted, the records stay put
+ *   (sort)        where the program is large enough to gain from it, the survivors are walked in the order of a 32-bit
+ *                 origin-cell / direction key that the shade kernels wrote next to every ray; only (key, entry) pairs are
+ *                 sorted, the records stay put
  *   k_extend      closest hit of every ray against the flat traversal program
  *                 (BvhNode::hit, hittable/bvh/mod.rs:86-101, unrolled -- rt_device.cuh)
  *   k_classify    bins the hits by material class into index lists
@@ -19,7 +21,7 @@
  *
  * Once every path has been generated and only a few thousand are alive, k_tail runs them to their end in one launch.
  * Queue lengths, the sample cursor and the ray counters live in a control block on the device (WaveCtl); the host
- * reads a 32-byte snapshot of it asynchronously every iteration and only uses it to stop issuing iterations.
+ * reads a 16-byte snapshot of it asynchronously every iteration and only uses it to size the sort and to stop issuing iterations.
  * Pixel sums are exact: every contribution is added as a 64-bit fixed-point integer (2^-32 units), so the sum does
  * not depend on the order in which paths end and the image is bit-reproducible (k_finish converts to float).
  * Randomness: one Philox slot stream per path, keyed (seed, pixel, sample) -- include/rt_rng.h.
