@@ -515,21 +515,24 @@ __device__ __forceinline__ bool shade_segment(const DScene &sc, const Ray &r, do
             Onb uvw = onb_from_w(rec.n); /* CosPdf::new(rec.normal), pdf.rs:35-39 */
             V3 direction;
             double pdf_val;
+            V3 unit_direction; /* direction.to_unit(): upstream forms it in CosPdf::value and again in scattering_pdf -- the same value */
             if (sc.n_light_roots == 0) {
                 /* Q12: empty `lights` -> the cosine pdf alone (decision shared with the oracle) */
                 direction = onb_local(uvw, random_cosine_direction(rng));
-                double c = dot(to_unit(direction), uvw.w);
+                unit_direction = to_unit(direction);
+                double c = dot(unit_direction, uvw.w);
                 pdf_val = c <= 0. ? 0. : c / RT_PI;
             } else {
                 if (rng.gen_range(0.0, 1.0) < 0.5) /* MixturePdf::generate, pdf.rs:95-101 */
                     direction = lights_random(lights_of(sc), rec.p, rng);
                 else
                     direction = onb_local(uvw, random_cosine_direction(rng));
-                double c = dot(to_unit(direction), uvw.w);
+                unit_direction = to_unit(direction);
+                double c = dot(unit_direction, uvw.w);
                 double cos_pdf = c <= 0. ? 0. : c / RT_PI;                            /* CosPdf::value, pdf.rs:46-53 */
                 pdf_val = 0.5 * lights_pdf_value(lights_of(sc), rec.p, direction) + 0.5 * cos_pdf; /* pdf.rs:102-104 */
             }
-            double cosine = dot(rec.n, to_unit(direction)); /* Lambertian::scattering_pdf, material/mod.rs:58-65 */
+            double cosine = dot(rec.n, unit_direction); /* Lambertian::scattering_pdf, material/mod.rs:58-65 */
             double spdf = cosine < 0. ? 0. : cosine / RT_PI;
             next.o = rec.p;
             next.d = direction;

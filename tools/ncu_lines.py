@@ -4,7 +4,8 @@
 
 LIB.so must be the very build the report was captured from (compiled with -lineinfo): its cubin is disassembled with
 `nvdisasm --print-line-info-inline` and joined with the report's SASS page by instruction offset.
-Prints, per source line (innermost inlined frame), warp instructions, stall samples and active lanes; then the same per function.
+Prints, per source line (innermost inlined frame; NCU_LINES_CALLER=1: the line that called it), warp instructions, stall samples
+and active lanes.
 """
 import collections, csv, os, re, subprocess, sys, tempfile
 
@@ -63,6 +64,8 @@ for cb in cubins:
             if not fresh:  # innermost frame that is this repo's code (not a CUDA header)
                 own = [f for f in stack if "/cuda/" not in f[0]] or stack
                 cur = (os.path.basename(own[0][0]), own[0][1], None)
+                if os.environ.get("NCU_LINES_CALLER") and len(own) > 1:  # attribute to the line that called the innermost frame
+                    cur = (os.path.basename(own[1][0]), own[1][1], None)
                 fresh = True
             if cur:
                 line_of[int(m.group(1), 16)] = cur
