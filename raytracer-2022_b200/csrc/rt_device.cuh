@@ -22,6 +22,7 @@
 #include "../../include/rt_rng.h"
 #include "../../include/rtgpu.h"
 #include "rt_cull.h"
+#include "rt_div.h"
 #include "rt_trig.h"
 
 #define RT_NO_HIT 0xffffffffu
@@ -45,7 +46,7 @@ __device__ __forceinline__ V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y -
 __device__ __forceinline__ V3 operator-(V3 a) { return V3{-a.x, -a.y, -a.z}; }
 __device__ __forceinline__ V3 operator*(V3 a, V3 b) { return V3{a.x * b.x, a.y * b.y, a.z * b.z}; }
 __device__ __forceinline__ V3 operator*(V3 a, double s) { return V3{a.x * s, a.y * s, a.z * s}; }
-__device__ __forceinline__ V3 operator/(V3 a, double s) { return V3{a.x / s, a.y / s, a.z / s}; }
+__device__ __forceinline__ V3 operator/(V3 a, double s) { return V3{rt_div_zero_fast(a.x, s), rt_div_zero_fast(a.y, s), rt_div_zero_fast(a.z, s)}; } /* rt_div.h */
 __device__ __forceinline__ double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ V3 cross(V3 a, V3 b) {
     return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
