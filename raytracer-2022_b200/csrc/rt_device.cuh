@@ -1220,7 +1220,7 @@ __device__ RT_LPDF_CALL double lights_pdf_value(const LightTable sc, V3 o, V3 v)
     if (sc.n_lights == sc.n_light_roots) { /* no HittableList inside `lights` (every reference scene): the same sums without the stack */
         double sum = 0.;
         for (uint32_t k = 0; k < sc.n_light_roots; ++k) sum += light_pdf_value(sc.lights[k], o, v);
-        return sum / (double)sc.n_light_roots;
+        return rt_div_zero_fast(sum, (double)sc.n_light_roots); /* 0 whenever the direction misses every light */
     }
     uint32_t at[RTGPU_MAX_LIGHT_NESTING + 1], end[RTGPU_MAX_LIGHT_NESTING + 1];
     double sum[RTGPU_MAX_LIGHT_NESTING + 1], len[RTGPU_MAX_LIGHT_NESTING + 1];
@@ -1242,7 +1242,7 @@ __device__ RT_LPDF_CALL double lights_pdf_value(const LightTable sc, V3 o, V3 v)
                 sum[sp] += light_pdf_value(l, o, v);
             }
         } else {
-            double val = sum[sp] / len[sp];
+            double val = rt_div_zero_fast(sum[sp], len[sp]);
             if (sp == 0) return val;
             --sp;
             sum[sp] += val;

@@ -284,6 +284,18 @@ def test_sincos_of_the_direction_sampling_is_within_one_ulp(tmp_path):
     assert r.returncode == 0 and "outside refused" in r.stdout, r.stdout + r.stderr
 
 
+def test_zero_numerator_short_cut_is_the_ieee_quotient(tmp_path):
+    """rt_div.h: `a / s` with a short cut for a == 0 (the device's div.rn.f64 sends a zero numerator through its ~100-instruction full
+    path; normals and directions with zero components divide zeros all the time).  Bit for bit `a / s` on special values crossed
+    with each other -- signed zeros, denormals, infinities, NaN, a zero divisor -- and on 2 M random operands."""
+    exe = str(tmp_path / "div_zero")
+    src = os.path.join(ROOT, "tests", "native", "div_zero.cpp")
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "div_zero ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_jpeg_writer_quality_100_roundtrip(tmp_path):
     """The output stage of main.rs:213-221 (JPEG at quality 100): host/jpeg_encode.cpp writes a baseline 4:4:4 stream that
     both this repo's decoder and libjpeg-turbo (PIL) read back to within 4 levels of the input (YCbCr rounding; every
