@@ -322,11 +322,14 @@ struct SortGrid {
 #define RT_SORT_DIR_BITS 8 /* direction below the octant: 8, 10, 12 = major axis + 2 x (3, 4, 5) bits, 6 = 2 x 3 bits, 0 = octant only */
 #endif
 constexpr int kSortKeyBits = 3 * RT_SORT_CELL_BITS + 3 + RT_SORT_DIR_BITS; /* radix passes = ceil(bits / 8) */
-__device__ __forceinline__ uint32_t spread_bits(uint32_t v) { /* RT_SORT_CELL_BITS bits -> every third bit */
-    uint32_t r = 0;
-#pragma unroll
-    for (int b = 0; b < RT_SORT_CELL_BITS; ++b) r |= ((v >> b) & 1u) << (3 * b);
-    return r;
+__device__ __forceinline__ uint32_t spread_bits(uint32_t v) { /* the low (up to 10) bits of v -> every third bit */
+    static_assert(RT_SORT_CELL_BITS <= 10, "spread_bits spreads at most 10 bits");
+    v &= (1u << RT_SORT_CELL_BITS) - 1u;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
 }
 __device__ __forceinline__ uint32_t ray_sort_key(const SortGrid &g, V3 ro, V3 rd) {
     float o[3] = {(float)ro.x, (float)ro.y, (float)ro.z};
