@@ -158,6 +158,36 @@ __device__ __forceinline__ rtgpu_xform load_xform(const TravScene &sc, uint32_t 
 #endif
 /* ---- primitive tests: return true and shrink `best` on a hit ------------------------------- */
 /* Sphere::hit, sphere.rs:39-56 (decision part; the record is rebuilt later for the winner) */
+/* The two queries ConstantMedium::hit makes of a Sphere boundary (constantmedium.rs:50-58): hit(r, -inf, inf) -> t1, then
+ * hit(r, t1 + 0.0001, inf) -> t2.  Both evaluate the same discriminant, square root and first root from the same operands, hence the
+ * same values: they are formed once.  The comparisons are the ones Sphere::hit makes, in its order (a NaN root passes them, as there). */
+__device__ __forceinline__ bool hit_sphere_twice(V3 o, V3 d, double a, V3 c, double radius, double &t1, bool &h2, double &t2) {
+    h2 = false;
+    V3 oc = o - c;
+    double half_b = dot(oc, d);
+    double cc = length_sqr(oc) - radius * radius;
+    double disc = half_b * half_b - a * cc;
+    if (disc < 0.) return false;
+    double sqrtd = sqrt(disc);
+    const double lo = (-half_b - sqrtd) / a;
+    /* first query: t_min = -inf, t_max = +inf */
+    double root = lo;
+    if (root < -CUDART_INF || CUDART_INF < root) {
+        root = (-half_b + sqrtd) / a;
+        if (root < -CUDART_INF || CUDART_INF < root) return false;
+    }
+    t1 = root;
+    /* second query: t_min = t1 + 0.0001, t_max = +inf */
+    const double tmin = t1 + 0.0001;
+    root = lo;
+    if (root < tmin || CUDART_INF < root) {
+        root = (-half_b + sqrtd) / a;
+        if (root < tmin || CUDART_INF < root) return true;
+    }
+    t2 = root;
+    h2 = true;
+    return true;
+}
 __device__ __forceinline__ bool hit_sphere(V3 o, V3 d, double a, V3 c, double radius, double tmin, double &best) {
     V3 oc = o - c;
     double half_b = dot(oc, d);
@@ -642,8 +672,7 @@ struct Traversal {
                     double bp[6];
                     load_op_payload(unit_ptr(sc.prog, i + 2), bp);
                     V3 c0 = v3(bp[0], bp[1], bp[2]);
-                    h1 = hit_sphere(o, d, a, c0, bp[3], -CUDART_INF, t1);
-                    if (h1) h2 = hit_sphere(o, d, a, c0, bp[3], t1 + 0.0001, t2);
+                    h1 = hit_sphere_twice(o, d, a, c0, bp[3], t1, h2, t2);
                 } else if constexpr (WALK_IN_LOOP) {
                     begin_boundary(sc, *mf);
                     return;
