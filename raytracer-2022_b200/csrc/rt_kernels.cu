@@ -286,7 +286,7 @@ struct QueueIO {
 };
 /* NEST 0: every ConstantMedium of the scene is bounded by one Sphere (intersected in line); NEST 1: some boundary has to be walked,
  * and the warp loop does it itself (Traversal<.., WALK_IN_LOOP>, any depth up to RT_MAX_MEDIUM_NESTING).  Picked at rtgpu_scene_create. */
-template <int NEST>
+template <int NEST, bool MESH>
 __global__ void __launch_bounds__(kThreads, NEST == 0 ? RT_EXTEND_MIN_BLOCKS0 : RT_EXTEND_MIN_BLOCKS) k_extend(DScene sc, PathQueue q, HitBuf hb, WaveCtl *ctl, int cur,
                                                                            WaveParams wp, const uint32_t *perm, uint32_t n_perm) {
     QueueIO io;
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, NEST == 0 ? RT_EXTEND_MIN_BLOCKS0 : 
     io.wp = wp;
     io.perm = perm;
     io.n_perm = perm ? n_perm : 0u;
-    extend_warp_loop<NEST>(trav_of(sc), sc.n_units, ctl->count[cur], &ctl->fetch, io);
+    extend_warp_loop<NEST, MESH>(trav_of(sc), sc.n_units, ctl->count[cur], &ctl->fetch, io);
 }
 
 /* ---- ray reordering between bounces ---------------------------------------------------------------
@@ -795,7 +795,7 @@ __global__ void __launch_bounds__(kThreads, NEST == 0 ? RT_EXTEND_MIN_BLOCKS0 : 
     io.t = t;
     io.op = op;
     io.rng_pos = rng_pos;
-    extend_warp_loop<NEST>(trav_of(sc), sc.n_units, n, fetch, io);
+    extend_warp_loop<NEST, true>(trav_of(sc), sc.n_units, n, fetch, io);
 }
 __global__ void __launch_bounds__(kThreads) k_trace_record(DScene sc, const rtgpu_ray *rays, const double *t, const uint32_t *op,
                                                            const uint32_t *rng_pos, rtgpu_hit *out, uint32_t n) {
@@ -939,6 +939,7 @@ struct rtgpu_scene : WaveRes {
     std::vector<void *> allocs;
     bool class_present[8] = {true, false, false, false, false, false, false, false};
     int medium_nesting = 0; /* deepest ConstantMedium-inside-a-boundary nesting of the program: picks the NEST of the walk kernels */
+    bool has_mesh = true;   /* the program holds Triangle or Ring ops: picks the MESH build of k_extend */
     int overlap = 1; /* RTGPU_OVERLAP=0: everything on one stream */
     int run_ahead = kRunAheadDefault; /* RTGPU_RUN_AHEAD: iterations the host may be ahead of the device (1 .. 32) */
     uint32_t tail_max = 1u << 16; /* RTGPU_TAIL_MAX: at most this many live paths are finished by k_tail in one launch (0 = never) */
@@ -976,8 +977,9 @@ struct SceneArena {
     rtgpu_status commit(rtgpu_scene *s);
 };
 
-rtgpu_status validate(const rtgpu_scene_desc *d, int *medium_nesting) {
+rtgpu_status validate(const rtgpu_scene_desc *d, int *medium_nesting, bool *has_mesh) {
     *medium_nesting = 0;
+    *has_mesh = false;
     auto bad = [](const char *m) {
         g_err = m;
         return RTGPU_ERR_INVALID_SCENE;
@@ -999,6 +1001,7 @@ rtgpu_status validate(const rtgpu_scene_desc *d, int *medium_nesting) {
         uint32_t kind = op.kind_ctx & 0xff, ctx = op.kind_ctx >> 8;
         uint32_t width = (kind == RTGPU_OP_MSPHERE || kind == RTGPU_OP_TRI) ? 2 : 1;
         if (i + width > d->n_ops) return bad("two-slot op at the end of the program");
+        if (kind == RTGPU_OP_TRI || kind == RTGPU_OP_RING) *has_mesh = true;
         switch (kind) {
         case RTGPU_OP_NODE:
             if (op.skip <= i || op.skip > d->n_ops) return bad("skip index out of range");
@@ -1320,8 +1323,13 @@ rtgpu_status run_paths(rtgpu_scene *s, const WaveParams &wp, const PathSink &sk,
         if (regen_aside) CK(cudaStreamWaitEvent(stream, s->side_ev[0], 0));
         phase_of_event.push_back(0);
         if ((st = mark()) != RTGPU_OK) return st;
-        if (s->medium_nesting >= 1) k_extend<1><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->ctl, cur, wp, perm, bound);
-        else k_extend<0><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->ctl, cur, wp, perm, bound);
+        if (s->medium_nesting >= 1) {
+            if (s->has_mesh) k_extend<1, true><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->ctl, cur, wp, perm, bound);
+            else k_extend<1, false><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->ctl, cur, wp, perm, bound);
+        } else {
+            if (s->has_mesh) k_extend<0, true><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->ctl, cur, wp, perm, bound);
+            else k_extend<0, false><<<blocks, kThreads, 0, stream>>>(s->d, qin, s->hb, s->ctl, cur, wp, perm, bound);
+        }
         CK(cudaGetLastError()); /* a failed extend launch must not let the shade kernels read stale hits */
         phase_of_event.push_back(1);
         if ((st = mark()) != RTGPU_OK) return st;
@@ -1459,7 +1467,8 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
     }
     *out = nullptr;
     int medium_nesting = 0;
-    rtgpu_status st = validate(desc, &medium_nesting);
+    bool has_mesh = true;
+    rtgpu_status st = validate(desc, &medium_nesting, &has_mesh);
     if (st != RTGPU_OK) return st;
     if (device >= 0) CK(cudaSetDevice(device));
     int cur = 0;
@@ -1468,6 +1477,7 @@ rtgpu_status rtgpu_scene_create(const rtgpu_scene_desc *desc, int device, rtgpu_
     if (!s) return RTGPU_ERR_OOM;
     s->device = cur;
     s->medium_nesting = medium_nesting;
+    s->has_mesh = has_mesh;
     if (cudaDeviceGetAttribute(&s->n_sm, cudaDevAttrMultiProcessorCount, cur) != cudaSuccess || s->n_sm < 1) {
         cudaGetLastError();
         s->n_sm = 148;
