@@ -42,7 +42,7 @@ for i in ids[lo:hi]:
     x = d[i]
     m = re.search(r"k_shade<(\d)>", x["name"])
     key = f"k_shade<{m.group(1)}>" if m else x["name"].split("(")[0].replace("<unnamed>::", "")[:60]
-    key = re.sub(r"^(?:void )?(k_extend|k_tail|k_trace_extend)<\d>$", r"\1", key)  # NEST instantiations
+    key = re.sub(r"^(?:void )?(k_extend|k_tail|k_trace_extend)<[^>]*>$", r"\1", key)  # NEST / MESH instantiations
     a = agg[key]
     a[0] += 1
     a[1] += x.get("gpu__time_duration.sum", 0)
