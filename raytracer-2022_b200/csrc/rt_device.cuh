@@ -710,7 +710,7 @@ struct Traversal {
                 xform_ray(xf, o, d);
             }
             ray.set_od(o, d);
-            derive(o, d, tmin, sc.extent);
+            derive(o, d, tmin, (float)p[0]); /* p[0]: the extent of the boxes under this wrapper, in the child's space (repack_program) */
             i += 2;
             break;
         }

@@ -1107,7 +1107,27 @@ rtgpu_status repack_program(const rtgpu_scene_desc *d, const std::vector<uint8_t
     boxes64.assign((size_t)(n_nodes ? n_nodes : 1) * 6, 0.);
     double ext = (double)RT_CULL_MIN_EXTENT;
     uint32_t ordinal = 0;
+    /* A PUSH hands its child a transformed ray, and the boxes under it live in the child's own space: the margin of the box
+     * pre-test there only has to cover THOSE boxes (rt_cull.h: B = the largest coordinate of any box the ray is tested against).
+     * A mesh modelled at unit size under Zoom / Translate would otherwise be tested with the margin of the whole scene -- hundreds
+     * of times its own -- and a quarter of its boxes would fall back to the f64 test.  Each PUSH carries its subtree's extent. */
+    struct OpenPush {
+        uint32_t end;   /* op index where the wrapper ends */
+        double ext;     /* largest |coordinate| of a NODE box seen under it so far */
+        uint32_t *unit; /* the PUSH's repacked unit */
+    };
+    std::vector<OpenPush> open;
+    auto close_pushes = [&](uint32_t upto) {
+        while (!open.empty() && upto >= open.back().end) {
+            OpenPush p = open.back();
+            open.pop_back();
+            double e = (p.ext == p.ext && p.ext <= 3e38) ? (double)nextafterf((float)p.ext, INFINITY) : (double)INFINITY;
+            memcpy(p.unit + 4, &e, 8); /* d[0] of the PUSH op: unused by the op itself */
+            if (!open.empty() && !(p.ext <= open.back().ext)) open.back().ext = p.ext; /* (an inner wrapper's boxes are not tested with the outer ray, but keeping the outer bound monotone costs nothing) */
+        }
+    };
     for (uint32_t i = 0; i < d->n_ops;) {
+        close_pushes(i);
         const rtgpu_op &op = d->ops[i];
         uint32_t kind = op.kind_ctx & 0xffu;
         uint32_t width = (kind == RTGPU_OP_MSPHERE || kind == RTGPU_OP_TRI) ? 2 : 1;
@@ -1121,15 +1141,21 @@ rtgpu_status repack_program(const rtgpu_scene_desc *d, const std::vector<uint8_t
                 boxes64[(size_t)ordinal * 6 + k] = op.d[k];
                 double a = op.d[k] < 0. ? -op.d[k] : op.d[k];
                 if (!(a <= ext)) ext = a; /* NaN or inf ends as an infinite extent: every box is then decided in f64 */
+                if (!open.empty() && !(a <= open.back().ext)) open.back().ext = a;
             }
             ++ordinal;
         } else {
             memcpy(w, &op, sizeof(rtgpu_op) * width);
-            if (kind == RTGPU_OP_MEDIUM || kind == RTGPU_OP_PUSH) w[1] = at[op.skip];
-            else if (kind != RTGPU_OP_POP) w[1] = mat_class[op.a]; /* a primitive has no skip: word 1 carries the shade class of its material */
+            if (kind == RTGPU_OP_MEDIUM || kind == RTGPU_OP_PUSH) {
+                w[1] = at[op.skip];
+                if (kind == RTGPU_OP_PUSH) open.push_back(OpenPush{op.skip, (double)RT_CULL_MIN_EXTENT, w});
+            } else if (kind != RTGPU_OP_POP) {
+                w[1] = mat_class[op.a]; /* a primitive has no skip: word 1 carries the shade class of its material */
+            }
         }
         i += width;
     }
+    close_pushes(d->n_ops);
     *extent = (ext == ext && ext <= 3e38) ? nextafterf((float)ext, INFINITY) : INFINITY;
     *n_units = u;
     return RTGPU_OK;
