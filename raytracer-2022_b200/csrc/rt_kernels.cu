@@ -1464,17 +1464,6 @@ rtgpu_status run_paths(rtgpu_scene *s, const WaveParams &wp, const PathSink &sk,
 
 extern "C" {
 
-#ifdef RT_DEBUG_COUNTERS
-int rtgpu_debug_counters(unsigned long long out[32], int reset) {
-    cudaMemcpyFromSymbol(out, g_dbg, sizeof(unsigned long long) * 32);
-    if (reset) {
-        unsigned long long z[32] = {0};
-        cudaMemcpyToSymbol(g_dbg, z, sizeof z);
-    }
-    return 0;
-}
-#endif
-
 const char *rtgpu_last_error(void) { return g_err.c_str(); }
 
 int rtgpu_device_count(void) {
