@@ -1149,6 +1149,11 @@ __device__ RT_TEX_CALL V3 texture_value(const TexTables sc, uint32_t id, double 
 }
 
 /* ---- random helpers (basic/vec.rs, basic/pdf.rs) --------------------------------------------- */
+/* `p.length() < 1.` of the rejection loops (vec.rs:72, :92), without the square root: for a correctly rounded sqrt,
+ * fl(sqrt(s)) < 1 <=> s < 1.  (s >= 1: sqrt(s) >= 1 and rounding is monotone.  s < 1: s <= 1 - 2^-53, and
+ * (1 - 2^-54)^2 = 1 - 2^-53 + 2^-108 > s, so sqrt(s) lies below the midpoint of 1 - 2^-53 and 1 and rounds to at most
+ * 1 - 2^-53.  NaN fails both comparisons.)  s itself is formed as length() forms it. */
+__device__ __forceinline__ bool length_below_one(V3 p) { return length_sqr(p) < 1.; }
 __device__ __forceinline__ V3 random_in_unit_sphere(rt_rng &rng) { /* vec.rs:69-76 */
     for (;;) {
         uint64_t ux, uy, uz;
@@ -1157,7 +1162,7 @@ __device__ __forceinline__ V3 random_in_unit_sphere(rt_rng &rng) { /* vec.rs:69-
         double y = -1. + (1. - -1.) * rt_rng::to_unit_f64(uy);
         double z = -1. + (1. - -1.) * rt_rng::to_unit_f64(uz);
         V3 p = v3(x, y, z);
-        if (length(p) < 1.) return p;
+        if (length_below_one(p)) return p;
     }
 }
 __device__ __forceinline__ V3 random_in_unit_disk(rt_rng &rng) { /* vec.rs:88-96 */
@@ -1165,7 +1170,7 @@ __device__ __forceinline__ V3 random_in_unit_disk(rt_rng &rng) { /* vec.rs:88-96
         double x = rng.gen_range(-1.0, 1.0);
         double y = rng.gen_range(-1.0, 1.0);
         V3 p = v3(x, y, 0.);
-        if (length(p) < 1.) return p;
+        if (length_below_one(p)) return p;
     }
 }
 __device__ __forceinline__ V3 random_cosine_direction(rt_rng &rng) { /* pdf.rs:12-21 */
