@@ -1462,6 +1462,33 @@ rtgpu_status run_paths(rtgpu_scene *s, const WaveParams &wp, const PathSink &sk,
 
 } // namespace
 
+namespace {
+/* Scratch of the entry points that have no scene to keep it in (rtgpu_resolve) or are parity probes (rtgpu_trace_batch,
+ * rtgpu_camera_rays): stream-ordered allocations from the device's default pool, which is told to keep what is freed -- the second
+ * call of a kind finds its buffers in the pool instead of going through cudaMalloc / cudaFree. */
+cudaError_t scratch_alloc(void **p, size_t bytes) {
+    static thread_local int tuned_device = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (tuned_device != dev) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+        tuned_device = dev;
+    }
+    return cudaMallocAsync(p, bytes ? bytes : 1, 0);
+}
+template <typename T>
+cudaError_t scratch_alloc(T **p, size_t bytes) { return scratch_alloc(reinterpret_cast<void **>(p), bytes); }
+void scratch_free(void *p) {
+    if (p) cudaFreeAsync(p, 0);
+}
+} // namespace
+
 extern "C" {
 
 const char *rtgpu_last_error(void) { return g_err.c_str(); }
@@ -1726,14 +1753,14 @@ rtgpu_status rtgpu_trace_batch(rtgpu_scene *s, const rtgpu_ray *rays, int64_t n,
     rtgpu_status st = RTGPU_OK;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     auto body = [&]() -> rtgpu_status {
-        CK(cudaMalloc(&d_rays, (size_t)n * sizeof(rtgpu_ray)));
-        CK(cudaMalloc(&d_out, (size_t)n * sizeof(rtgpu_hit)));
-        CK(cudaMalloc(&d_t, (size_t)n * sizeof(double)));
-        CK(cudaMalloc(&d_u32, ((size_t)2 * n + 1) * sizeof(uint32_t)));
+        CK(scratch_alloc(&d_rays, (size_t)n * sizeof(rtgpu_ray)));
+        CK(scratch_alloc(&d_out, (size_t)n * sizeof(rtgpu_hit)));
+        CK(scratch_alloc(&d_t, (size_t)n * sizeof(double)));
+        CK(scratch_alloc(&d_u32, ((size_t)2 * n + 1) * sizeof(uint32_t)));
         CK(cudaMemset(d_u32 + 2 * n, 0, sizeof(uint32_t)));
         CK(cudaMemcpy(d_rays, rays, (size_t)n * sizeof(rtgpu_ray), cudaMemcpyHostToDevice));
         if (keys) {
-            CK(cudaMalloc(&d_keys, (size_t)n * sizeof(uint64_t)));
+            CK(scratch_alloc(&d_keys, (size_t)n * sizeof(uint64_t)));
             CK(cudaMemcpy(d_keys, keys, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice));
         }
         CK(cudaEventCreate(&e0));
@@ -1754,11 +1781,11 @@ rtgpu_status rtgpu_trace_batch(rtgpu_scene *s, const rtgpu_ray *rays, int64_t n,
         return RTGPU_OK;
     };
     st = body();
-    if (d_rays) cudaFree(d_rays);
-    if (d_keys) cudaFree(d_keys);
-    if (d_out) cudaFree(d_out);
-    if (d_t) cudaFree(d_t);
-    if (d_u32) cudaFree(d_u32);
+    scratch_free(d_rays);
+    scratch_free(d_keys);
+    scratch_free(d_out);
+    scratch_free(d_t);
+    scratch_free(d_u32);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     return st;
@@ -1774,8 +1801,8 @@ rtgpu_status rtgpu_camera_rays(rtgpu_scene *s, int32_t width, int32_t height, in
     rtgpu_ray *d_out = nullptr;
     uint32_t *d_pos = nullptr;
     auto body = [&]() -> rtgpu_status {
-        CK(cudaMalloc(&d_out, (size_t)n * sizeof(rtgpu_ray)));
-        CK(cudaMalloc(&d_pos, (size_t)n * sizeof(uint32_t)));
+        CK(scratch_alloc(&d_out, (size_t)n * sizeof(rtgpu_ray)));
+        CK(scratch_alloc(&d_pos, (size_t)n * sizeof(uint32_t)));
         WaveParams wp;
         wp.seed = seed;
         wp.first_pixel = (uint32_t)first_pixel;
@@ -1791,8 +1818,8 @@ rtgpu_status rtgpu_camera_rays(rtgpu_scene *s, int32_t width, int32_t height, in
         return RTGPU_OK;
     };
     rtgpu_status st = body();
-    if (d_out) cudaFree(d_out);
-    if (d_pos) cudaFree(d_pos);
+    scratch_free(d_out);
+    scratch_free(d_pos);
     return st;
 }
 
@@ -1850,19 +1877,19 @@ rtgpu_status rtgpu_resolve(const float *accum, int32_t width, int32_t height, in
     auto body = [&]() -> rtgpu_status {
         const float *src = accum;
         if (!accum_on_device) {
-            CK(cudaMalloc(&d_acc, npix * 3 * sizeof(float)));
+            CK(scratch_alloc(&d_acc, npix * 3 * sizeof(float)));
             CK(cudaMemcpy(d_acc, accum, npix * 3 * sizeof(float), cudaMemcpyHostToDevice));
             src = d_acc;
         }
-        CK(cudaMalloc(&d_rgb, npix * 3));
+        CK(scratch_alloc(&d_rgb, npix * 3));
         k_resolve<<<(unsigned)((npix + 255) / 256), 256>>>(src, width, height, spp, d_rgb);
         CK(cudaGetLastError());
         CK(cudaMemcpy(rgb8, d_rgb, npix * 3, cudaMemcpyDeviceToHost));
         return RTGPU_OK;
     };
     rtgpu_status st = body();
-    if (d_acc) cudaFree(d_acc);
-    if (d_rgb) cudaFree(d_rgb);
+    scratch_free(d_acc);
+    scratch_free(d_rgb);
     return st;
 }
 
